@@ -1,0 +1,707 @@
+// K1 — LEDDetector::findLeds on the GPU (reference: monocular_pose_estimator_lib/src/led_detector.cpp:35-112).
+//
+//   find_leds_kernel   (K1a)  threshold-to-zero + 8-bit fixed-point Gaussian + "blurred != 0" mask, fused.
+//                             HBM-bound: every ROI byte is read exactly once from DRAM through TMA
+//                             (cp.async.bulk.tensor) into a multi-stage shared-memory ring; nothing but a
+//                             sparse 1-bit mask (rows that contain foreground) and one flag word per tile
+//                             is written back.
+//   extract_blobs_kernel (K1b) external contours (cv::findContours RETR_EXTERNAL / CHAIN_APPROX_NONE),
+//                             contourArea / boundingRect / moments, the four shape filters and
+//                             cv::undistortPoints, one warp per frame working on the sparse mask.
+//
+// Bit-exact contract (pinned against cv2 4.13):
+//   blur    taps = getGaussianKernelBitExact -> 8.8 fixed point (sum 256), horizontal pass 8.8, vertical
+//           pass 16.16, out = (acc + 32768) >> 16, BORDER_REFLECT_101 at the ROI edge.
+//   contour Suzuki border following as OpenCV's icvFetchContour (start at the component's raster-first
+//           pixel, clockwise search from NW for the closing point, counter-clockwise search afterwards),
+//           components enclosed by another component are not reported, output in reverse raster order of
+//           the start pixels.
+//
+// Why the blur is evaluated sparsely: a blurred pixel can only be non-zero if a thresholded pixel within
+// the (2R+1)^2 window is non-zero.  The dense phase therefore only asks "does this 16-byte unit contain a
+// byte > threshold" (about 0.4 instructions per pixel, SWAR on OR-ed words) — at 23 B/clk/SM of HBM
+// bandwidth a dense 25-tap fixed-point blur (>10 instructions per pixel) would be issue-bound at ~1/3 of
+// the memory roofline.  Only words whose neighbourhood is "hot" run the exact fixed-point arithmetic, and
+// its result is identical to the dense evaluation.
+#include "mpe_internal.cuh"
+
+namespace mpe {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX wrappers (TMA + mbarrier)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 3-D tiled TMA load: tensor (x: u32 elements along a row, y: image row, z: frame) -> dense smem box.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+// cv::BORDER_REFLECT_101 index into [0, n)
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+  }
+  return p;
+}
+
+// "does any byte of w exceed the threshold" — exact SWAR test.
+//   T < 128 : byte > T  <=>  bit7(byte) | bit7((byte & 0x7f) + (127 - T))
+//   T >= 128: byte > T  <=>  bit7(byte) & bit7((byte & 0x7f) + (255 - T))
+template <bool kLow>
+__device__ __forceinline__ uint32_t any_byte_gt(uint32_t w, uint32_t k) {
+  uint32_t x = (w & 0x7f7f7f7fu) + k;
+  return (kLow ? (x | w) : (x & w)) & 0x80808080u;
+}
+
+__device__ __forceinline__ int floor_div4(int v) { return v >> 2; }   // arithmetic shift = floor for negatives
+
+struct TileCoord {
+  int f, s, ct;
+  Roi roi;
+  bool valid;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const K1Geom& g, int t) {
+  TileCoord c;
+  int per_frame = g.n_strips * g.n_ct;
+  c.f = t / per_frame;
+  int rem = t - c.f * per_frame;
+  c.s = rem / g.n_ct;
+  c.ct = rem - c.s * g.n_ct;
+  c.roi = g.rois ? g.rois[c.f] : g.roi;
+  c.valid = (c.s * kTileRows < c.roi.h) && (c.ct * g.tw_px < c.roi.w);
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a
+// ------------------------------------------------------------------------------------------------
+// Shared-memory layout (dynamic):
+//   [0, 64)                              mbarriers (one per stage)
+//   hot   [rows][hot_wpr]   u32          exact "word holds a byte > thr" bits of the current tile
+//   omask [kTileRows][om_wpr] u32        non-zero bits of the blurred output rows of the current tile
+//   misc  [4] u32                        list length, row-flag accumulator
+//   list  [kTileRows * box_w] u16        compacted (row, word) pairs that need the exact blur
+//   stage ring: kStages x rows x box_w u32 (1024-byte aligned start)
+struct K1Smem {
+  uint64_t* bars;
+  uint32_t* hot;
+  uint32_t* omask;
+  uint32_t* misc;
+  uint16_t* list;
+  uint8_t* ring;
+};
+
+__host__ __device__ inline size_t k1_ring_offset(int rows, int box_w, int tw_px) {
+  int hot_wpr = (box_w + 31) >> 5;
+  int om_wpr = (tw_px + 31) >> 5;
+  size_t off = 64 + (size_t)(rows * hot_wpr + kTileRows * om_wpr + 4) * 4 + (size_t)kTileRows * box_w * 2;
+  return (off + 1023) & ~(size_t)1023;
+}
+
+template <int R, bool kLowThr, int kStages>
+__global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_constant__ CUtensorMap tmap, const K1aArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const K1Geom& g = a.g;
+  constexpr int kRows = kTileRows + 2 * R;
+  const int box_w = g.box_w;                       // u32 per smem row
+  const int row_bytes = box_w * 4;
+  const int hot_wpr = (box_w + 31) >> 5;
+  const int om_wpr = (g.tw_px + 31) >> 5;
+  const uint32_t stage_bytes = (uint32_t)(kRows * row_bytes);
+
+  K1Smem sm;
+  sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
+  sm.hot = reinterpret_cast<uint32_t*>(smem_raw + 64);
+  sm.omask = sm.hot + kRows * hot_wpr;
+  sm.misc = sm.omask + kTileRows * om_wpr;
+  sm.list = reinterpret_cast<uint16_t*>(sm.misc + 4);
+  sm.ring = smem_raw + k1_ring_offset(kRows, box_w, g.tw_px);
+
+  const int tid = threadIdx.x;
+  const int n_tiles = g.n_frames * g.n_strips * g.n_ct;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // producer state (thread 0 only): next tile to look at, number of valid tiles issued so far
+  int ptile = blockIdx.x, pcount = 0;
+  auto produce_one = [&]() {
+    while (ptile < n_tiles) {
+      TileCoord c = decode_tile(g, ptile);
+      ptile += gridDim.x;
+      if (!c.valid) continue;
+      int stage = pcount % kStages;
+      int x_elem0 = floor_div4(c.roi.x + c.ct * g.tw_px - R);
+      int y0 = c.roi.y + c.s * kTileRows - R;
+      mbar_expect_tx(&sm.bars[stage], stage_bytes);
+      tma_load_3d(sm.ring + (size_t)stage * stage_bytes, &tmap, &sm.bars[stage], x_elem0, y0, c.f);
+      ++pcount;
+      return;
+    }
+  };
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) produce_one();
+
+  const uint32_t thr_k = (uint32_t)a.thr_k;
+  const int units_per_row = box_w >> 2;
+  const int n_units = kRows * units_per_row;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  int ccount = 0;   // valid tiles consumed by this CTA
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    TileCoord c = decode_tile(g, tile);
+    if (!c.valid) continue;
+    const int stage = ccount % kStages;
+    const uint32_t parity = (uint32_t)((ccount / kStages) & 1);
+    ++ccount;
+    mbar_wait(&sm.bars[stage], parity);
+    const uint8_t* tile_smem = sm.ring + (size_t)stage * stage_bytes;
+
+    // ---------------- dense phase: is anything above the threshold in this tile? ----------------
+    uint32_t local_hot = 0;
+    const uint4* units = reinterpret_cast<const uint4*>(tile_smem);
+    for (int u = tid; u < n_units; u += kK1Threads) {
+      uint4 v = units[u];
+      uint32_t o = (v.x | v.y) | (v.z | v.w);
+      local_hot |= any_byte_gt<kLowThr>(o, thr_k);
+    }
+    int any_hot = __syncthreads_or((int)local_hot);
+
+    const int x_elem0 = floor_div4(c.roi.x + c.ct * g.tw_px - R);
+    const int y0 = c.roi.y + c.s * kTileRows - R;
+    const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
+    uint32_t* flag_ptr = a.rowflags + (size_t)c.f * g.flags_per_frame + c.s * g.n_ct + c.ct;
+
+    if (!any_hot) {
+      if (tid == 0) *flag_ptr = 0u;
+    } else {
+      // ---------------- sparse phase ----------------
+      for (int i = tid; i < kRows * hot_wpr + kTileRows * om_wpr + 4; i += kK1Threads) sm.hot[i] = 0u;   // hot, omask, misc are contiguous
+      __syncthreads();
+      // exact per-word hot bits
+      for (int u = tid; u < n_units; u += kK1Threads) {
+        uint4 v = units[u];
+        uint32_t o = (v.x | v.y) | (v.z | v.w);
+        if (any_byte_gt<kLowThr>(o, thr_k)) {
+          int row = u / units_per_row;
+          int w0 = (u - row * units_per_row) * 4;
+          uint32_t bits = (any_byte_gt<kLowThr>(v.x, thr_k) ? 1u : 0u) | (any_byte_gt<kLowThr>(v.y, thr_k) ? 2u : 0u) |
+                          (any_byte_gt<kLowThr>(v.z, thr_k) ? 4u : 0u) | (any_byte_gt<kLowThr>(v.w, thr_k) ? 8u : 0u);
+          if (bits) atomicOr(&sm.hot[row * hot_wpr + (w0 >> 5)], bits << (w0 & 31));
+        }
+      }
+      __syncthreads();
+      // words whose (2R+1) x 3-word source neighbourhood holds a hot word: vertical OR, horizontal dilation
+      for (int item = tid; item < out_rows * hot_wpr; item += kK1Threads) {
+        int r = item / hot_wpr, hw = item - r * hot_wpr;
+        uint32_t v = 0, vl = 0, vr = 0;
+#pragma unroll
+        for (int dr = 0; dr <= 2 * R; ++dr) {
+          const uint32_t* hrow = sm.hot + (r + dr) * hot_wpr;
+          v |= hrow[hw];
+          if (hw > 0) vl |= hrow[hw - 1];
+          if (hw + 1 < hot_wpr) vr |= hrow[hw + 1];
+        }
+        uint32_t d = v | (v << 1) | (v >> 1) | (vl >> 31) | (vr << 31);
+        while (d) {
+          int bit = __ffs(d) - 1;
+          d &= d - 1;
+          int j = hw * 32 + bit;
+          if (j < box_w) {
+            uint32_t slot = atomicAdd(&sm.misc[0], 1u);
+            sm.list[slot] = (uint16_t)((r << 8) | j);
+          }
+        }
+      }
+      __syncthreads();
+      const int n_list = (int)sm.misc[0];
+      const int tile_x0 = c.roi.x + c.ct * g.tw_px;                      // output pixel range of this tile
+      const int tile_x1 = min(c.roi.x + c.roi.w, tile_x0 + g.tw_px);
+      const uint32_t thr = (uint32_t)a.threshold;
+      for (int e = tid; e < n_list; e += kK1Threads) {
+        const int r = sm.list[e] >> 8, j = sm.list[e] & 0xff;
+        const int first_px = 4 * x_elem0 + 4 * j;                        // image x of the word's first pixel
+        if (first_px + 3 < tile_x0 || first_px >= tile_x1) continue;
+        const int Y = y0 + R + r;                                        // image row of this output row
+        const bool interior = (first_px - R >= c.roi.x) && (first_px + 3 + R < c.roi.x + c.roi.w) &&
+                              (Y - R >= c.roi.y) && (Y + R < c.roi.y + c.roi.h);
+        // horizontal pass for the 2R+1 source rows, 4 output pixels each (8.8 fixed point)
+        uint32_t hsum[2 * R + 1][4];
+#pragma unroll
+        for (int dr = 0; dr <= 2 * R; ++dr) {
+          uint32_t px[4 + 2 * R];
+          if (interior) {
+            const uint8_t* src = tile_smem + (size_t)(r + dr) * row_bytes + (4 * j - R);
+#pragma unroll
+            for (int k = 0; k < 4 + 2 * R; ++k) px[k] = src[k];
+          } else {
+            int yy = c.roi.y + reflect101(Y + dr - R - c.roi.y, c.roi.h);
+            const uint8_t* srow = tile_smem + (size_t)(yy - y0) * row_bytes;
+#pragma unroll
+            for (int k = 0; k < 4 + 2 * R; ++k) {
+              int xx = c.roi.x + reflect101(first_px + k - R - c.roi.x, c.roi.w);
+              px[k] = srow[xx - 4 * x_elem0];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4 + 2 * R; ++k) px[k] = (px[k] > thr) ? px[k] : 0u;      // cv::THRESH_TOZERO, strict >
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) acc += a.taps[k] * px[q + k];
+            hsum[dr][q] = acc;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int X = first_px + q;
+          if (X < tile_x0 || X >= tile_x1) continue;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int dr = 0; dr <= 2 * R; ++dr) acc += a.taps[dr] * hsum[dr][q];
+          if ((acc + 32768u) >> 16) {                                     // 16.16 -> u8 round-half-up, non-zero?
+            int bx = X - tile_x0;
+            atomicOr(&sm.omask[r * om_wpr + (bx >> 5)], 1u << (bx & 31));
+          }
+        }
+      }
+      __syncthreads();
+      // write-out: one warp per row; rows without foreground are not written (their flag bit stays 0)
+      const int words_per_ct = g.tw_px >> 5;   // only used when n_ct > 1 (tw_px is a multiple of 32 then)
+      for (int r = warp; r < out_rows; r += kK1Threads / 32) {
+        uint32_t nz = 0;
+        for (int w = lane; w < om_wpr; w += 32) nz |= sm.omask[r * om_wpr + w];
+        if (__ballot_sync(0xffffffffu, nz != 0)) {
+          uint32_t* dst = a.mask + ((size_t)c.f * g.mask_rows + (c.s * kTileRows + r)) * g.mask_wpr + c.ct * words_per_ct;
+          for (int w = lane; w < om_wpr; w += 32) dst[w] = sm.omask[r * om_wpr + w];
+          if (lane == 0) atomicOr(&sm.misc[1], 1u << r);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) *flag_ptr = sm.misc[1];
+    }
+    // every thread is past a barrier that follows its last read of this stage: refill it
+    if (tid == 0) produce_one();
+  }
+}
+
+size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages) {
+  int rows = kTileRows + 2 * radius;
+  return k1_ring_offset(rows, g.box_w, g.tw_px) + (size_t)stages * rows * g.box_w * 4;
+}
+
+template <int R, bool kLow, int kStages>
+static cudaError_t launch_k1a_inst(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
+  size_t smem = find_leds_smem_bytes(a.g, R, kStages);
+  auto kern = find_leds_kernel<R, kLow, kStages>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
+  int ctas_per_sm = (smem <= 110 * 1024) ? 2 : 1;
+  int grid = n_tiles < n_sms * ctas_per_sm ? n_tiles : n_sms * ctas_per_sm;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kK1Threads, smem, st>>>(tmap, a);
+  return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_k1a_r(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
+  // stage count: as many as fit in ~105 KB so that two CTAs share an SM
+  size_t s4 = find_leds_smem_bytes(a.g, R, 4), s3 = find_leds_smem_bytes(a.g, R, 3);
+  bool low = a.threshold < 128;
+  if (s4 <= 110 * 1024) return low ? launch_k1a_inst<R, true, 4>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 4>(a, tmap, n_sms, st);
+  if (s3 <= 110 * 1024) return low ? launch_k1a_inst<R, true, 3>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 3>(a, tmap, n_sms, st);
+  return low ? launch_k1a_inst<R, true, 2>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 2>(a, tmap, n_sms, st);
+}
+
+cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st) {
+  switch (radius) {
+    case 1: return launch_k1a_r<1>(a, tmap, n_sms, st);
+    case 2: return launch_k1a_r<2>(a, tmap, n_sms, st);
+    case 3: return launch_k1a_r<3>(a, tmap, n_sms, st);
+    case 4: return launch_k1a_r<4>(a, tmap, n_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b — contours, moments, filters, undistortion.  One warp per frame.
+// ------------------------------------------------------------------------------------------------
+struct MaskView {
+  const uint32_t* flags;   // this frame's row-flag words
+  const uint32_t* mask;    // this frame's mask rows
+  int w, h;                // ROI size
+  int n_ct, roi_n_ct, tw_px, wpr, words_per_ct;
+};
+
+__device__ __forceinline__ uint32_t mv_word(const MaskView& m, int y, int wi) {
+  // word wi of ROI row y, 0 where the producing tile reported no foreground in that row
+  if ((unsigned)y >= (unsigned)m.h || wi < 0 || wi >= m.wpr) return 0u;
+  int ct = (m.roi_n_ct == 1) ? 0 : min(wi / m.words_per_ct, m.roi_n_ct - 1);
+  uint32_t fl = m.flags[(y >> 5) * m.n_ct + ct];
+  if (!((fl >> (y & 31)) & 1u)) return 0u;
+  return __ldg(m.mask + (size_t)y * m.wpr + wi);
+}
+__device__ __forceinline__ bool mv_bit(const MaskView& m, int x, int y) {
+  if ((unsigned)x >= (unsigned)m.w || (unsigned)y >= (unsigned)m.h) return false;
+  return (mv_word(m, y, x >> 5) >> (x & 31)) & 1u;
+}
+
+// direction codes as OpenCV: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE
+__device__ __forceinline__ int dir_dx(int s) { return (s == 0 || s == 1 || s == 7) ? 1 : ((s == 3 || s == 4 || s == 5) ? -1 : 0); }
+__device__ __forceinline__ int dir_dy(int s) { return (s == 1 || s == 2 || s == 3) ? -1 : ((s == 5 || s == 6 || s == 7) ? 1 : 0); }
+
+struct Contour {
+  long long a00, a10, a01;
+  int minx, maxx, miny, maxy;
+  int status;   // 1 accepted (true outer border of a component), 0 rejected, -1 step limit hit
+};
+
+// Follow the border that starts at (x0,y0) (a pixel whose W, NW, N, NE neighbours are background) exactly as
+// icvFetchContour does for an outer border.  The candidate is rejected as soon as the border reaches a pixel
+// that precedes the start in raster order: then (x0,y0) is not the first pixel of its component (the border
+// is either the component's outer border seen from a later "tip", or the border of a hole).
+// When (px,py) is given (px >= 0) the even-odd crossing number of the closed polygon with respect to that
+// lattice point is returned in *inside.
+__device__ Contour trace_border(const MaskView& m, int x0, int y0, int px, int py, bool* inside) {
+  Contour c;
+  c.a00 = c.a10 = c.a01 = 0;
+  c.minx = c.maxx = x0;
+  c.miny = c.maxy = y0;
+  c.status = 1;
+  bool in = false;
+  int s = 4, s_end = 4;
+  do {
+    s = (s - 1) & 7;
+    if (mv_bit(m, x0 + dir_dx(s), y0 + dir_dy(s))) break;
+  } while (s != s_end);
+  if (s == s_end) {   // isolated pixel: one-point contour, all sums zero
+    if (inside) *inside = false;
+    return c;
+  }
+  const int i1x = x0 + dir_dx(s), i1y = y0 + dir_dy(s);
+  int cx = x0, cy = y0;           // i3
+  int prevx = 0, prevy = 0;       // previously emitted point
+  bool have_prev = false;
+  const long long step_limit = 4ll * m.w * m.h + 16;
+  long long steps = 0;
+  for (;;) {
+    int nx, ny;
+    do {
+      s = (s + 1) & 7;
+      nx = cx + dir_dx(s);
+      ny = cy + dir_dy(s);
+    } while (!mv_bit(m, nx, ny));
+    // emit (cx,cy)
+    if (have_prev) {
+      long long dxy = (long long)prevx * cy - (long long)cx * prevy;
+      c.a00 += dxy;
+      c.a10 += dxy * (prevx + cx);
+      c.a01 += dxy * (prevy + cy);
+      if (px >= 0 && ((prevy > py) != (cy > py))) {
+        int xi = (prevy == py) ? prevx : cx;     // the endpoint lying on row py
+        if (px < xi) in = !in;
+      }
+    }
+    prevx = cx; prevy = cy; have_prev = true;
+    c.minx = min(c.minx, cx); c.maxx = max(c.maxx, cx);
+    c.miny = min(c.miny, cy); c.maxy = max(c.maxy, cy);
+    if (nx == x0 && ny == y0 && cx == i1x && cy == i1y) break;
+    if (ny < y0 || (ny == y0 && nx < x0)) { c.status = 0; break; }
+    if (++steps > step_limit) { c.status = -1; break; }
+    cx = nx; cy = ny;
+    s = (s + 4) & 7;
+  }
+  if (c.status == 1) {   // closing edge: last emitted point -> start
+    long long dxy = (long long)prevx * y0 - (long long)x0 * prevy;
+    c.a00 += dxy;
+    c.a10 += dxy * (prevx + x0);
+    c.a01 += dxy * (prevy + y0);
+    if (px >= 0 && ((prevy > py) != (y0 > py))) {
+      int xi = (prevy == py) ? prevx : x0;
+      if (px < xi) in = !in;
+    }
+  }
+  if (inside) *inside = in;
+  return c;
+}
+
+// candidate starts in word wi of row y: foreground pixels whose W, NW, N and NE neighbours are background
+__device__ __forceinline__ uint32_t candidate_bits(const MaskView& m, int y, int wi) {
+  uint32_t cur = mv_word(m, y, wi);
+  if (!cur) return 0u;
+  uint32_t curL = mv_word(m, y, wi - 1);
+  uint32_t up = mv_word(m, y - 1, wi), upL = mv_word(m, y - 1, wi - 1), upR = mv_word(m, y - 1, wi + 1);
+  uint32_t Wn = (cur << 1) | (curL >> 31);
+  uint32_t NW = (up << 1) | (upL >> 31);
+  uint32_t NE = (up >> 1) | (upR << 31);
+  return cur & ~Wn & ~up & ~NW & ~NE;
+}
+
+// Is the component starting at (px,py) enclosed by another component?  (RETR_EXTERNAL drops it then.)
+// Fast exits: a clear axis ray from the start pixel to the ROI edge proves it is not enclosed.
+__device__ bool is_enclosed(const MaskView& m, int px, int py) {
+  // left / right rays in the same row
+  {
+    bool blocked_l = false, blocked_r = false;
+    int wi0 = px >> 5, b = px & 31;
+    for (int wi = 0; wi <= wi0 && !blocked_l; ++wi) {
+      uint32_t v = mv_word(m, py, wi);
+      if (wi == wi0) v &= (b == 0) ? 0u : (0xffffffffu >> (32 - b));
+      blocked_l = v != 0;
+    }
+    if (!blocked_l) return false;
+    // the component itself extends to the right of its start pixel; skip its own run first
+    int x = px;
+    while (x < m.w && mv_bit(m, x, py)) ++x;
+    for (; x < m.w && !blocked_r; ++x) blocked_r = mv_bit(m, x, py);
+    if (!blocked_r) return false;
+  }
+  {
+    bool blocked_u = false;
+    for (int y = py - 1; y >= 0 && !blocked_u; --y) blocked_u = mv_bit(m, px, y);
+    if (!blocked_u) return false;
+    // downwards the ray first leaves through the component's own pixels; a later foreground pixel may still
+    // belong to the component itself, so a blocked ray proves nothing — fall through to the exact test.
+  }
+  // exact test: any component whose first pixel precedes row py and whose outer polygon contains (px,py)
+  const int strips = (m.h + kTileRows - 1) / kTileRows;
+  for (int s = 0; s < strips && s * kTileRows < py; ++s) {
+    uint32_t fl = 0;
+    for (int ct = 0; ct < m.roi_n_ct; ++ct) fl |= m.flags[s * m.n_ct + ct];
+    while (fl) {
+      int r = __ffs(fl) - 1;
+      fl &= fl - 1;
+      int y = s * kTileRows + r;
+      if (y >= py) break;
+      for (int wi = 0; wi < m.wpr; ++wi) {
+        uint32_t cand = candidate_bits(m, y, wi);
+        while (cand) {
+          int b = __ffs(cand) - 1;
+          cand &= cand - 1;
+          bool inside = false;
+          Contour c = trace_border(m, wi * 32 + b, y, px, py, &inside);
+          if (c.status == 1 && inside) return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+// cv::undistortPoints(src, dst, K, D, noArray(), P = K), default criteria (5 fixed-point iterations)
+__device__ __forceinline__ void undistort_point(const DevCamera& cam, float sx, float sy, float* ox, float* oy) {
+  const double fx = cam.K[0], fy = cam.K[4], cx = cam.K[2], cy = cam.K[5];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = sx, y = sy;
+  const double u = x, v = y;
+  x = (x - cx) * ifx;
+  y = (y - cy) * ify;
+  if (cam.nD > 0) {
+    const double* k = cam.D;
+    double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+      double r2 = x * x + y * y;
+      double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) {
+        x = (u - cx) * ifx;
+        y = (v - cy) * ify;
+        break;
+      }
+      double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+  }
+  double xx = cam.K[0] * x + cam.K[1] * y + cam.K[2];
+  double yy = cam.K[3] * x + cam.K[4] * y + cam.K[5];
+  double ww = 1. / (cam.K[6] * x + cam.K[7] * y + cam.K[8]);
+  *ox = (float)(xx * ww);
+  *oy = (float)(yy * ww);
+}
+
+constexpr int kBlobWarpsPerCta = 4;
+
+struct WarpScratch {
+  int cand_x[kCandCap];
+  int cand_y[kCandCap];
+  int n_cand;
+  int n_kept;
+  int flags;
+  int kept_key[MPE_MAX_BLOBS];     // raster index of the contour start (sort key)
+  float kept_cx[MPE_MAX_BLOBS];
+  float kept_cy[MPE_MAX_BLOBS];
+};
+
+__device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane) {
+  __syncwarp();
+  int n = min(ws.n_cand, kCandCap);
+  for (int base = 0; base < n; base += 32) {
+    int i = base + lane;
+    if (i < n) {
+      int x0 = ws.cand_x[i], y0 = ws.cand_y[i];
+      Contour c = trace_border(m, x0, y0, -1, -1, nullptr);
+      if (c.status == -1) atomicOr(&ws.flags, MPE_F_TRACE_ABORT);
+      if (c.status == 1 && !is_enclosed(m, x0, y0)) {
+        // led_detector.cpp:67-81
+        double area = fabs((double)c.a00) * 0.5;                       // cv::contourArea
+        int rw = c.maxx - c.minx + 1, rh = c.maxy - c.miny + 1;      // cv::boundingRect
+        // cv::moments(contour): m00 = a00 * (+-0.5), m10 = a10 * (+-1/6), m01 = a01 * (+-1/6), sign so that m00 > 0
+        double m00 = 0, m10 = 0, m01 = 0;
+        if (c.a00 != 0) {
+          double db1_2 = (c.a00 > 0) ? 0.5 : -0.5;
+          double db1_6 = (c.a00 > 0) ? 0.16666666666666666666666666666667 : -0.16666666666666666666666666666667;
+          m00 = (double)c.a00 * db1_2;
+          m10 = (double)c.a10 * db1_6;
+          m01 = (double)c.a01 * db1_6;
+        }
+        float mcx = (float)(m10 / m00) + (float)roi.x;                  // Point2f(m10/m00, m01/m00) + Point2f(ROI.x, ROI.y)
+        float mcy = (float)(m01 / m00) + (float)roi.y;
+        const double pi = 3.1415926535897932384626433832795;
+        double wh = fabs(1 - fmin((double)rw / (double)rh, (double)rh / (double)rw));
+        double hw2 = (double)(rw / 2), hh2 = (double)(rh / 2);          // integer division, led_detector.cpp:80-81
+        double cw = fabs(1 - (area / (pi * (hw2 * hw2))));
+        double ch = fabs(1 - (area / (pi * (hh2 * hh2))));
+        bool keep = area >= a.bp.min_blob_area && area <= a.bp.max_blob_area && wh <= a.bp.max_width_height_distortion &&
+                    cw <= a.bp.max_circular_distortion && ch <= a.bp.max_circular_distortion;
+        if (keep) {
+          int slot = atomicAdd(&ws.n_kept, 1);
+          if (slot < MPE_MAX_BLOBS) {
+            ws.kept_key[slot] = y0 * m.w + x0;
+            ws.kept_cx[slot] = mcx;
+            ws.kept_cy[slot] = mcy;
+          } else {
+            atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) ws.n_cand = 0;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(const K1bArgs a) {
+  __shared__ WarpScratch scratch[kBlobWarpsPerCta];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kBlobWarpsPerCta + warp;
+  if (f >= a.g.n_frames) return;
+  WarpScratch& ws = scratch[warp];
+  const K1Geom& g = a.g;
+  const Roi roi = g.rois ? g.rois[f] : g.roi;
+
+  MaskView m;
+  m.flags = a.rowflags + (size_t)f * g.flags_per_frame;
+  m.mask = a.mask + (size_t)f * g.mask_rows * g.mask_wpr;
+  m.w = roi.w; m.h = roi.h;
+  m.n_ct = g.n_ct;                 // row flags are stored with the launch-wide n_ct stride
+  m.roi_n_ct = (roi.w + g.tw_px - 1) / g.tw_px;
+  m.tw_px = g.tw_px;
+  m.wpr = g.mask_wpr;
+  m.words_per_ct = g.tw_px >> 5;
+  const int roi_wpr = (roi.w + 31) >> 5;
+  const int roi_n_ct = m.roi_n_ct;
+  const int roi_strips = (roi.h + kTileRows - 1) / kTileRows;
+
+  if (lane == 0) { ws.n_cand = 0; ws.n_kept = 0; ws.flags = 0; }
+  __syncwarp();
+
+  // ---- scan the rows that contain foreground, collect contour-start candidates ----
+  for (int s = 0; s < roi_strips; ++s) {
+    uint32_t fl = 0;
+    for (int ct = 0; ct < roi_n_ct; ++ct) fl |= m.flags[s * g.n_ct + ct];
+    while (fl) {
+      int r = __ffs(fl) - 1;
+      fl &= fl - 1;
+      int y = s * kTileRows + r;
+      for (int wbase = 0; wbase < roi_wpr; wbase += 32) {
+        int wi = wbase + lane;
+        uint32_t cand = (wi < roi_wpr) ? candidate_bits(m, y, wi) : 0u;
+        if (wi == roi_wpr - 1 && (roi.w & 31)) cand &= 0xffffffffu >> (32 - (roi.w & 31));
+        while (cand) {
+          int b = __ffs(cand) - 1;
+          cand &= cand - 1;
+          int slot = atomicAdd(&ws.n_cand, 1);
+          if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + b; ws.cand_y[slot] = y; }
+          else atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
+        }
+        __syncwarp();
+        if (ws.n_cand >= 32) process_candidates(m, a, roi, ws, lane);
+      }
+    }
+  }
+  if (ws.n_cand > 0) process_candidates(m, a, roi, ws, lane);
+  __syncwarp();
+
+  // ---- order: cv::findContours returns the contours in reverse raster order of their start pixels ----
+  const int n = min(ws.n_kept, MPE_MAX_BLOBS);
+  for (int i = lane; i < n; i += 32) {
+    int key = ws.kept_key[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (ws.kept_key[j] > key) ? 1 : 0;
+    float ux, uy;
+    undistort_point(a.cam, ws.kept_cx[i], ws.kept_cy[i], &ux, &uy);      // led_detector.cpp:97-110
+    size_t o = ((size_t)f * MPE_MAX_BLOBS + rank) * 2;
+    a.centers[o] = ws.kept_cx[i];
+    a.centers[o + 1] = ws.kept_cy[i];
+    a.det[o] = (double)ux;
+    a.det[o + 1] = (double)uy;
+  }
+  if (lane == 0) {
+    a.n_det[f] = n;
+    a.flags[f] = ws.flags;
+  }
+}
+
+cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
+  int grid = (a.g.n_frames + kBlobWarpsPerCta - 1) / kBlobWarpsPerCta;
+  extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace mpe

@@ -1,0 +1,721 @@
+// C-ABI implementation (include/mpe_b200.h): context, configuration, stage calls and the batch drivers.
+// Host code only orchestrates: every arithmetic step of the hot path runs in the CUDA kernels of
+// k1_find_leds.cu / k2_p3p_sweep.cu / k3_validate_refine.cu.  There is no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mpe_internal.cuh"
+
+using namespace mpe;
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DevBuffers {
+  uint8_t* frames = nullptr;       // [max_batch][max_h][pitch]
+  uint32_t* rowflags = nullptr;    // [max_batch][flags_per_frame]
+  uint32_t* mask = nullptr;        // [max_batch][max_h][mask_wpr]
+  int* n_det = nullptr;            // [max_batch]
+  int* flags = nullptr;            // [max_batch]
+  double* det = nullptr;           // [max_batch][MPE_MAX_BLOBS][2]
+  float* centers = nullptr;        // [max_batch][MPE_MAX_BLOBS][2]
+  uint32_t* hist = nullptr;        // [max_batch][MPE_MAX_DET*MPE_MAX_LEDS]
+  uint32_t* done = nullptr;        // [max_batch]
+  uint32_t* corr = nullptr;        // [max_batch][2*MPE_MAX_LEDS]
+  int* n_corr = nullptr;           // [max_batch]
+  double* pose = nullptr;          // [max_batch][16]
+  double* cov = nullptr;           // [max_batch][36]
+  int* ok = nullptr;               // [max_batch]
+  int* iters = nullptr;            // [max_batch]
+  int* updated = nullptr;          // [max_batch]
+  Roi* rois = nullptr;             // [max_batch]
+  mpe_result* results = nullptr;   // [max_batch]
+  double* scratch_d = nullptr;     // p3p stage call
+};
+
+}  // namespace
+
+struct mpe_ctx {
+  int device = 0;
+  int n_sms = 148;
+  int max_batch = 0, max_w = 0, max_h = 0;
+  int pitch = 0;                  // device frame pitch (multiple of 16)
+  int mask_wpr = 0, flags_per_frame = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  DevBuffers d;
+  mpe_result* h_results = nullptr;   // pinned
+  // configuration
+  bool have_camera = false, have_markers = false, have_params = false;
+  DevCamera cam{};
+  DevPoseParams pp{};
+  mpe_params params{};
+  // instrumentation
+  bool timing = false;
+  cudaEvent_t ev[8]{};
+  float kernel_ms[4] = {0, 0, 0, 0};
+  bool timing_pending = false;
+  long long launches = 0;
+  std::string err;
+  PFN_encodeTiled encode = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+};
+
+namespace {
+
+int fail(mpe_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(ctx, MPE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// OpenCV getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED for CV_8U (ksize from sigma:
+// cvRound(sigma*6+1)|1), 8 fractional bits, centre tap = 256 - sum(others).  Verified against cv2 4.13
+// impulse responses and full-image blurs for sigma in [0.3, 6] (tests/test_blur_model.py).
+bool gaussian_taps_8u(double sigma, int* radius, uint32_t taps[kMaxTaps]) {
+  if (!(sigma > 0)) return false;
+  int n = (int)std::nearbyint(sigma * 6 + 1) | 1;
+  int n2 = (n - 1) / 2;
+  if (n2 < 1 || n2 > kMaxRadius) return false;
+  std::vector<double> vals(n2);
+  double scale2x = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < n2; ++i) {
+    double x = (double)(i - n2);
+    vals[i] = std::exp(scale2x * x * x);
+    sum += vals[i];
+  }
+  sum = 2 * sum + 1.0;
+  double mul = 1.0 / sum;
+  double err = 0;
+  long long tot = 0;
+  for (int i = 0; i < n2; ++i) {
+    double adj = vals[i] * mul * 256.0 + err;
+    long long v0 = (long long)std::nearbyint(adj);
+    err = adj - (double)v0;
+    taps[i] = (uint32_t)v0;
+    taps[n - 1 - i] = (uint32_t)v0;
+    tot += 2 * v0;
+  }
+  taps[n2] = (uint32_t)(256 - tot);
+  *radius = n2;
+  return true;
+}
+
+// Combinations::numCombinations with the reference's unsigned factorial (combinations.cpp:34-45)
+unsigned factorial_u(int N) { return (N == 1 || N == 0) ? 1u : factorial_u(N - 1) * (unsigned)N; }
+unsigned num_combinations_ref(unsigned N, unsigned K) { return factorial_u((int)N) / (factorial_u((int)K) * factorial_u((int)(N - K))); }
+
+struct FrameSource {
+  const uint8_t* base;      // device pointer of frame 0
+  int pitch;                // bytes per row (multiple of 16)
+  long long frame_stride;   // bytes between frames (multiple of 16)
+  int width, height;
+  int n_frames_total;       // frames addressable from base
+};
+
+int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_h, int radius, K1Geom* g) {
+  g->img_w = w; g->img_h = h;
+  g->roi = roi; g->rois = nullptr;
+  g->max_roi_w = max_roi_w; g->max_roi_h = max_roi_h;
+  g->n_strips = (max_roi_h + kTileRows - 1) / kTileRows;
+  int tw = max_roi_w;
+  if (tw > kMaxTileWidthPx) tw = kMaxTileWidthPx;          // 960 = 30 mask words
+  g->n_ct = (max_roi_w + tw - 1) / tw;
+  if (g->n_ct > 1) tw = kMaxTileWidthPx;
+  g->tw_px = tw;
+  // widest span of u32 elements a tile can touch: [floor((x - R)/4), floor((x + tw + R - 1)/4)] for any x
+  int span = (tw + 2 * radius + 3 + 3) / 4 + 1;
+  g->box_w = (span + 3) & ~3;
+  if (g->box_w > 256) return MPE_E_UNSUPPORTED;
+  g->mask_wpr = c->mask_wpr;
+  g->mask_rows = c->max_h;
+  g->flags_per_frame = c->flags_per_frame;
+  if (g->n_strips * g->n_ct > g->flags_per_frame) return MPE_E_CAPACITY;
+  if (g->n_ct * ((tw + 31) / 32) > g->mask_wpr && g->n_ct > 1) return MPE_E_CAPACITY;
+  return MPE_OK;
+}
+
+int encode_tensor_map(mpe_ctx* c, const FrameSource& src, int box_w, int rows, CUtensorMap* out) {
+  if (!c->encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) return fail(c, MPE_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    c->encode = (PFN_encodeTiled)fn;
+  }
+  if ((src.pitch & 15) || (src.frame_stride & 15) || ((uintptr_t)src.base & 15))
+    return fail(c, MPE_E_INVALID, "device frames must be 16-byte aligned with pitch and frame stride multiples of 16");
+  cuuint64_t gdim[3] = {(cuuint64_t)(src.pitch / 4), (cuuint64_t)src.height, (cuuint64_t)src.n_frames_total};
+  cuuint64_t gstride[2] = {(cuuint64_t)src.pitch, (cuuint64_t)src.frame_stride};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = c->encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)src.base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, MPE_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return MPE_OK;
+}
+
+void time_begin(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) cudaEventRecord(c->ev[2 * k], st); }
+void time_end(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) { cudaEventRecord(c->ev[2 * k + 1], st); c->timing_pending = true; } }
+
+// K1a + K1b over frames [f0, f0+n) of `src`, outputs into slots [slot0, slot0+n) of the context buffers.
+int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, Roi roi, const Roi* rois_dev, cudaStream_t st) {
+  int radius = 0;
+  K1aArgs a{};
+  if (!gaussian_taps_8u(c->params.gaussian_sigma, &radius, a.taps))
+    return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "]");
+  int max_w = rois_dev ? src.width : roi.w, max_h = rois_dev ? src.height : roi.h;
+  int rc = make_geometry(c, src.width, src.height, roi, max_w, max_h, radius, &a.g);
+  if (rc != MPE_OK) return fail(c, rc, "ROI / image too large for this context");
+  a.g.n_frames = n;
+  a.g.rois = rois_dev;
+  CUtensorMap tmap;
+  FrameSource sub = src;
+  sub.base = src.base + (size_t)f0 * src.frame_stride;
+  sub.n_frames_total = n;
+  rc = encode_tensor_map(c, sub, a.g.box_w, kTileRows + 2 * radius, &tmap);
+  if (rc != MPE_OK) return rc;
+  int T = c->params.threshold_value;
+  if (T < 0) T = 0;                  // THRESH_TOZERO with a negative threshold keeps every pixel; so does "> 0" (0 stays 0)
+  if (T > 255) T = 255;              // nothing is > 255
+  a.threshold = T;
+  a.thr_k = (T < 128) ? (127 - T) * 0x01010101 : (255 - T) * 0x01010101;
+  a.rowflags = c->d.rowflags + (size_t)slot0 * c->flags_per_frame;
+  a.mask = c->d.mask + (size_t)slot0 * c->max_h * c->mask_wpr;
+  time_begin(c, 0, st);
+  CUDA_TRY(c, launch_find_leds(a, tmap, radius, c->n_sms, st));
+  time_end(c, 0, st);
+  ++c->launches;
+
+  K1bArgs b{};
+  b.g = a.g;
+  b.rowflags = a.rowflags;
+  b.mask = a.mask;
+  b.cam = c->cam;
+  b.bp.min_blob_area = c->params.min_blob_area;
+  b.bp.max_blob_area = c->params.max_blob_area;
+  b.bp.max_width_height_distortion = c->params.max_width_height_distortion;
+  b.bp.max_circular_distortion = c->params.max_circular_distortion;
+  b.n_det = c->d.n_det + slot0;
+  b.flags = c->d.flags + slot0;
+  b.det = c->d.det + (size_t)slot0 * MPE_MAX_BLOBS * 2;
+  b.centers = c->d.centers + (size_t)slot0 * MPE_MAX_BLOBS * 2;
+  time_begin(c, 1, st);
+  CUDA_TRY(c, launch_extract_blobs(b, st));
+  time_end(c, 1, st);
+  ++c->launches;
+  return MPE_OK;
+}
+
+int choose_split(const mpe_ctx* c, int n_frames) {
+  int n = c->pp.n_obj;
+  long long est = (long long)n * (n - 1) * (n - 2) / 6 * n * (n - 1) * (n - 2);
+  long long by_work = (est + 255) / 256;
+  long long by_fill = (4LL * c->n_sms + n_frames - 1) / n_frames;
+  long long s = by_work < by_fill ? by_work : by_fill;
+  if (s < 1) s = 1;
+  if (s > 128) s = 128;
+  return (int)s;
+}
+
+int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* active) {
+  K2Args k{};
+  k.n_frames = n;
+  k.n_det = c->d.n_det + slot0;
+  k.det = c->d.det + (size_t)slot0 * MPE_MAX_BLOBS * 2;
+  k.det_stride = MPE_MAX_BLOBS;
+  k.cam = c->cam;
+  k.pp = c->pp;
+  k.split = choose_split(c, n);
+  k.hist = c->d.hist + (size_t)slot0 * MPE_MAX_DET * MPE_MAX_LEDS;
+  k.done_counter = c->d.done + slot0;
+  k.corr = c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS;
+  k.n_corr = c->d.n_corr + slot0;
+  k.frame_flags = c->d.flags + slot0;
+  k.active = active;
+  CUDA_TRY(c, cudaMemsetAsync(k.hist, 0, (size_t)n * MPE_MAX_DET * MPE_MAX_LEDS * sizeof(uint32_t), st));
+  CUDA_TRY(c, cudaMemsetAsync(k.done_counter, 0, (size_t)n * sizeof(uint32_t), st));
+  time_begin(c, 2, st);
+  CUDA_TRY(c, launch_p3p_sweep(k, st));
+  time_end(c, 2, st);
+  ++c->launches;
+  return MPE_OK;
+}
+
+int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const uint8_t* active) {
+  K3Args k{};
+  k.n_frames = n;
+  k.n_det = c->d.n_det + slot0;
+  k.det = c->d.det + (size_t)slot0 * MPE_MAX_BLOBS * 2;
+  k.det_stride = MPE_MAX_BLOBS;
+  k.cam = c->cam;
+  k.pp = c->pp;
+  k.corr = c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS;
+  k.n_corr = c->d.n_corr + slot0;
+  k.mode = mode;
+  k.pose_io = c->d.pose + (size_t)slot0 * 16;
+  k.cov = c->d.cov + (size_t)slot0 * 36;
+  k.ok = c->d.ok + slot0;
+  k.iters = c->d.iters + slot0;
+  k.updated = c->d.updated + slot0;
+  k.active = active;
+  time_begin(c, 3, st);
+  CUDA_TRY(c, launch_validate_refine(k, st));
+  time_end(c, 3, st);
+  ++c->launches;
+  return MPE_OK;
+}
+
+__global__ void pack_results_kernel(int n, Roi roi, const int* n_det, const int* flags, const double* det, const float* centers,
+                                    const uint32_t* corr, const int* n_corr, const double* pose, const double* cov, const int* ok,
+                                    const int* iters, const int* updated, mpe_result* out) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  mpe_result r;
+  r.updated = updated[f];
+  r.n_det = n_det[f];
+  r.n_corr = n_corr[f];
+  r.gn_iters = iters[f];
+  r.flags = flags[f];
+  r.init_ok = ok[f];
+  r.roi.x = roi.x; r.roi.y = roi.y; r.roi.width = roi.w; r.roi.height = roi.h;
+  for (int i = 0; i < 16; ++i) r.pose[i] = pose[(size_t)f * 16 + i];
+  for (int i = 0; i < 36; ++i) r.cov[i] = cov[(size_t)f * 36 + i];
+  for (int i = 0; i < 2 * MPE_MAX_LEDS; ++i) r.corr[i] = (i < 2 * r.n_corr) ? corr[(size_t)f * 2 * MPE_MAX_LEDS + i] : 0u;
+  int nd = r.n_det < MPE_MAX_DET ? r.n_det : MPE_MAX_DET;
+  for (int i = 0; i < 2 * MPE_MAX_DET; ++i) {
+    r.det[i] = (i < 2 * nd) ? det[(size_t)f * MPE_MAX_BLOBS * 2 + i] : 0.0;
+    r.centers[i] = (i < 2 * nd) ? centers[(size_t)f * MPE_MAX_BLOBS * 2 + i] : 0.f;
+  }
+  out[f] = r;
+}
+
+// The whole cold path for frames [f0, f0+n) of src -> device results slots [slot0, slot0+n)
+int run_cold(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, cudaStream_t st) {
+  Roi full{0, 0, src.width, src.height};                       // pose_estimator.cpp:72
+  int rc = run_find_leds(c, src, f0, n, slot0, full, nullptr, st);
+  if (rc != MPE_OK) return rc;
+  rc = run_sweep(c, slot0, n, st, nullptr);                    // setImagePoints + initialise (histogram + decode)
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(c->d.pose + (size_t)slot0 * 16, 0, (size_t)n * 16 * sizeof(double), st));
+  CUDA_TRY(c, cudaMemsetAsync(c->d.cov + (size_t)slot0 * 36, 0, (size_t)n * 36 * sizeof(double), st));
+  rc = run_refine(c, slot0, n, 0, st, nullptr);                // checkCorrespondences + optimisePose
+  if (rc != MPE_OK) return rc;
+  pack_results_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, full, c->d.n_det + slot0, c->d.flags + slot0,
+                                                       c->d.det + (size_t)slot0 * MPE_MAX_BLOBS * 2, c->d.centers + (size_t)slot0 * MPE_MAX_BLOBS * 2,
+                                                       c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS, c->d.n_corr + slot0, c->d.pose + (size_t)slot0 * 16,
+                                                       c->d.cov + (size_t)slot0 * 36, c->d.ok + slot0, c->d.iters + slot0, c->d.updated + slot0,
+                                                       c->d.results + slot0);
+  CUDA_TRY(c, cudaGetLastError());
+  ++c->launches;
+  return MPE_OK;
+}
+
+int check_configured(mpe_ctx* c, bool need_markers) {
+  if (!c) return MPE_E_INVALID;
+  if (!c->have_camera) return fail(c, MPE_E_NOT_CONFIGURED, "camera not set (mpe_set_camera)");
+  if (!c->have_params) return fail(c, MPE_E_NOT_CONFIGURED, "parameters not set (mpe_set_params)");
+  if (need_markers && !c->have_markers) return fail(c, MPE_E_NOT_CONFIGURED, "markers not set (mpe_set_markers)");
+  return MPE_OK;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_height) {
+  if (!out || max_batch < 1 || max_width < 8 || max_height < 1) return MPE_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MPE_E_CUDA;
+  mpe_ctx* c = new mpe_ctx();
+  c->device = device;
+#define CREATE_TRY(expr)                                                           \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      fprintf(stderr, "mpe_create: %s: %s\n", #expr, cudaGetErrorString(_e));      \
+      mpe_destroy(c);                                                              \
+      return MPE_E_CUDA;                                                           \
+    }                                                                              \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  c->n_sms = prop.multiProcessorCount;
+  c->max_batch = max_batch; c->max_w = max_width; c->max_h = max_height;
+  c->pitch = (max_width + 15) & ~15;
+  int n_ct = (max_width + kMaxTileWidthPx - 1) / kMaxTileWidthPx;
+  c->mask_wpr = (n_ct > 1) ? n_ct * (kMaxTileWidthPx / 32) : (max_width + 31) / 32;
+  c->flags_per_frame = ((max_height + kTileRows - 1) / kTileRows) * n_ct;
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  size_t B = (size_t)max_batch;
+  CREATE_TRY(dev_alloc(&c->d.frames, B * c->pitch * max_height));
+  CREATE_TRY(dev_alloc(&c->d.rowflags, B * c->flags_per_frame));
+  CREATE_TRY(dev_alloc(&c->d.mask, B * max_height * c->mask_wpr));
+  CREATE_TRY(dev_alloc(&c->d.n_det, B));
+  CREATE_TRY(dev_alloc(&c->d.flags, B));
+  CREATE_TRY(dev_alloc(&c->d.det, B * MPE_MAX_BLOBS * 2));
+  CREATE_TRY(dev_alloc(&c->d.centers, B * MPE_MAX_BLOBS * 2));
+  CREATE_TRY(dev_alloc(&c->d.hist, B * MPE_MAX_DET * MPE_MAX_LEDS));
+  CREATE_TRY(dev_alloc(&c->d.done, B));
+  CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
+  CREATE_TRY(dev_alloc(&c->d.n_corr, B));
+  CREATE_TRY(dev_alloc(&c->d.pose, B * 16));
+  CREATE_TRY(dev_alloc(&c->d.cov, B * 36));
+  CREATE_TRY(dev_alloc(&c->d.ok, B));
+  CREATE_TRY(dev_alloc(&c->d.iters, B));
+  CREATE_TRY(dev_alloc(&c->d.updated, B));
+  CREATE_TRY(dev_alloc(&c->d.rois, B));
+  CREATE_TRY(dev_alloc(&c->d.results, B));
+  CREATE_TRY(cudaMemset(c->d.n_corr, 0, B * sizeof(int)));
+  CREATE_TRY(cudaMemset(c->d.flags, 0, B * sizeof(int)));
+  CREATE_TRY(cudaMemset(c->d.corr, 0, B * 2 * MPE_MAX_LEDS * sizeof(uint32_t)));
+  CREATE_TRY(cudaMemset(c->d.rowflags, 0, B * c->flags_per_frame * sizeof(uint32_t)));
+  CREATE_TRY(cudaMallocHost((void**)&c->h_results, B * sizeof(mpe_result)));
+  for (int i = 0; i < 8; ++i) CREATE_TRY(cudaEventCreate(&c->ev[i]));
+  // PoseEstimator::PoseEstimator() defaults (pose_estimator.cpp:36-39)
+  c->pp.back_projection_pixel_tolerance = 3;
+  c->pp.nearest_neighbour_pixel_tolerance = 5;
+  c->pp.certainty_threshold = 0.75;
+  c->pp.valid_correspondence_threshold = 0.7;
+  c->params.back_projection_pixel_tolerance = 3;
+  c->params.nearest_neighbour_pixel_tolerance = 5;
+  c->params.certainty_threshold = 0.75;
+  c->params.valid_correspondence_threshold = 0.7;
+#undef CREATE_TRY
+  *out = c;
+  return MPE_OK;
+}
+
+void mpe_destroy(mpe_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
+  cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.done); cudaFree(c->d.corr);
+  cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.scratch_d);
+  if (c->h_results) cudaFreeHost(c->h_results);
+  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (auto e : c->chunk_events) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+const char* mpe_last_error(const mpe_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int mpe_set_stream(mpe_ctx* c, void* cuda_stream) {
+  if (!c) return MPE_E_INVALID;
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return MPE_OK;
+}
+
+int mpe_set_camera(mpe_ctx* c, const double K[9], const double* D, int nD) {
+  if (!c || !K) return MPE_E_INVALID;
+  if (!(nD == 0 || nD == 4 || nD == 5 || nD == 8 || nD == 12)) return fail(c, MPE_E_UNSUPPORTED, "distortion vector must have 0, 4, 5, 8 or 12 coefficients");
+  if (nD > 0 && !D) return MPE_E_INVALID;
+  for (int i = 0; i < 9; ++i) c->cam.K[i] = K[i];
+  for (int i = 0; i < MPE_MAX_DIST; ++i) c->cam.D[i] = (i < nD) ? D[i] : 0.0;
+  c->cam.nD = nD;
+  c->have_camera = true;
+  return MPE_OK;
+}
+
+int mpe_set_markers(mpe_ctx* c, const double* xyz, int n) {
+  if (!c || !xyz || n < 1 || n > MPE_MAX_LEDS) return fail(c, MPE_E_INVALID, "marker count must be in [1, MPE_MAX_LEDS]");
+  c->pp.n_obj = n;
+  for (int i = 0; i < 3 * n; ++i) c->pp.markers[i] = xyz[i];
+  c->pp.histogram_threshold = (n >= 3) ? num_combinations_ref((unsigned)n, 3u) : 0u;   // pose_estimator.cpp:54
+  c->have_markers = true;
+  return MPE_OK;
+}
+
+int mpe_set_params(mpe_ctx* c, const mpe_params* p) {
+  if (!c || !p) return MPE_E_INVALID;
+  int radius;
+  uint32_t taps[kMaxTaps];
+  if (!gaussian_taps_8u(p->gaussian_sigma, &radius, taps))
+    return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "] (sigma in about (0.09, 1.41))");
+  c->params = *p;
+  c->pp.back_projection_pixel_tolerance = p->back_projection_pixel_tolerance;
+  c->pp.nearest_neighbour_pixel_tolerance = p->nearest_neighbour_pixel_tolerance;
+  c->pp.certainty_threshold = p->certainty_threshold;
+  c->pp.valid_correspondence_threshold = p->valid_correspondence_threshold;
+  c->have_params = true;
+  return MPE_OK;
+}
+
+int mpe_set_histogram_threshold(mpe_ctx* c, uint32_t t) { if (!c) return MPE_E_INVALID; c->pp.histogram_threshold = t; return MPE_OK; }
+uint32_t mpe_get_histogram_threshold(const mpe_ctx* c) { return c ? c->pp.histogram_threshold : 0u; }
+
+int mpe_synchronize(mpe_ctx* c) {
+  if (!c) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------- stage calls
+int mpe_find_leds(mpe_ctx* c, const uint8_t* image, int pitch, int width, int height, mpe_rect roi, double* px_out,
+                  float* centers_out, int* n_out, int* flags_out) {
+  int rc = check_configured(c, false);
+  if (rc != MPE_OK) return rc;
+  if (!image || !n_out || width < 1 || height < 1 || pitch < width) return fail(c, MPE_E_INVALID, "bad image arguments");
+  if (width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "image larger than the context capacity");
+  if (roi.x < 0 || roi.y < 0 || roi.width < 1 || roi.height < 1 || roi.x + roi.width > width || roi.y + roi.height > height)
+    return fail(c, MPE_E_INVALID, "ROI outside the image (cv::Mat::operator() would throw)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames, c->pitch, image, pitch, width, height, cudaMemcpyHostToDevice, st));
+  FrameSource src{c->d.frames, c->pitch, (long long)c->pitch * c->max_h, width, height, 1};
+  Roi r{roi.x, roi.y, roi.width, roi.height};
+  rc = run_find_leds(c, src, 0, 1, 0, r, nullptr, st);
+  if (rc != MPE_OK) return rc;
+  int n = 0, fl = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&n, c->d.n_det, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(&fl, c->d.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (n > MPE_MAX_BLOBS) n = MPE_MAX_BLOBS;
+  if (n > 0) {
+    if (px_out) CUDA_TRY(c, cudaMemcpy(px_out, c->d.det, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (centers_out) CUDA_TRY(c, cudaMemcpy(centers_out, c->d.centers, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  *n_out = n;
+  if (flags_out) *flags_out = fl;
+  return MPE_OK;
+}
+
+static int upload_detections(mpe_ctx* c, const double* det, int n_det, cudaStream_t st) {
+  if (n_det < 0 || n_det > MPE_MAX_DET || (n_det > 0 && !det)) return fail(c, MPE_E_INVALID, "n_det must be in [0, MPE_MAX_DET]");
+  if (n_det > 0) CUDA_TRY(c, cudaMemcpyAsync(c->d.det, det, (size_t)n_det * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.n_det, &n_det, sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemsetAsync(c->d.flags, 0, sizeof(int), st));
+  return MPE_OK;
+}
+
+static int upload_correspondences(mpe_ctx* c, const uint32_t* corr, int k, cudaStream_t st) {
+  if (k < 0 || k > MPE_MAX_LEDS || (k > 0 && !corr)) return fail(c, MPE_E_INVALID, "k must be in [0, MPE_MAX_LEDS]");
+  for (int i = 0; i < k; ++i) {
+    if (corr[2 * i] < 1 || corr[2 * i] > (uint32_t)c->pp.n_obj) return fail(c, MPE_E_INVALID, "correspondence LED index out of range");
+  }
+  if (k > 0) CUDA_TRY(c, cudaMemcpyAsync(c->d.corr, corr, (size_t)k * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.n_corr, &k, sizeof(int), cudaMemcpyHostToDevice, st));
+  return MPE_OK;
+}
+
+int mpe_initialise(mpe_ctx* c, const double* det, int n_det, uint32_t* hist_out, uint32_t* corr_out, int* k_out, double pose_out[16], int* ok) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  rc = upload_detections(c, det, n_det, st);
+  if (rc != MPE_OK) return rc;
+  int zero = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.n_corr, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = run_sweep(c, 0, 1, st, nullptr);
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(c->d.pose, 0, 16 * sizeof(double), st));
+  rc = run_refine(c, 0, 1, 1, st, nullptr);
+  if (rc != MPE_OK) return rc;
+  int k = 0, okv = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&k, c->d.n_corr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(&okv, c->d.ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (hist_out && n_det > 0) CUDA_TRY(c, cudaMemcpy(hist_out, c->d.hist, (size_t)n_det * c->pp.n_obj * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (corr_out && k > 0) CUDA_TRY(c, cudaMemcpy(corr_out, c->d.corr, (size_t)k * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (pose_out) CUDA_TRY(c, cudaMemcpy(pose_out, c->d.pose, 16 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (k_out) *k_out = k;
+  if (ok) *ok = okv;
+  return MPE_OK;
+}
+
+int mpe_check_correspondences(mpe_ctx* c, const double* det, int n_det, const uint32_t* corr, int k, double pose_out[16], int* ok) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  rc = upload_detections(c, det, n_det, st);
+  if (rc != MPE_OK) return rc;
+  rc = upload_correspondences(c, corr, k, st);
+  if (rc != MPE_OK) return rc;
+  for (int i = 0; i < k; ++i)
+    if (corr[2 * i + 1] < 1 || corr[2 * i + 1] > (uint32_t)n_det) return fail(c, MPE_E_INVALID, "checkCorrespondences needs detection indices in [1, n_det]");
+  CUDA_TRY(c, cudaMemsetAsync(c->d.pose, 0, 16 * sizeof(double), st));
+  rc = run_refine(c, 0, 1, 1, st, nullptr);
+  if (rc != MPE_OK) return rc;
+  int okv = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&okv, c->d.ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (pose_out) CUDA_TRY(c, cudaMemcpy(pose_out, c->d.pose, 16 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ok) *ok = okv;
+  return MPE_OK;
+}
+
+int mpe_optimise_pose(mpe_ctx* c, const double* det, int n_det, const uint32_t* corr, int k, double pose_io[16], double cov_out[36], int* iters_out) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!pose_io) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  rc = upload_detections(c, det, n_det, st);
+  if (rc != MPE_OK) return rc;
+  rc = upload_correspondences(c, corr, k, st);
+  if (rc != MPE_OK) return rc;
+  for (int i = 0; i < k; ++i)
+    if (corr[2 * i + 1] > (uint32_t)n_det) return fail(c, MPE_E_INVALID, "detection index out of range");
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.pose, pose_io, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = run_refine(c, 0, 1, 2, st, nullptr);
+  if (rc != MPE_OK) return rc;
+  int it = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&it, c->d.iters, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  CUDA_TRY(c, cudaMemcpy(pose_io, c->d.pose, 16 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cov_out) CUDA_TRY(c, cudaMemcpy(cov_out, c->d.cov, 36 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (iters_out) *iters_out = it;
+  return MPE_OK;
+}
+
+int mpe_p3p_compute_poses(mpe_ctx* c, const double* feature_vectors, const double* world_points, int n, double* solutions, int* status) {
+  if (!c || n < 0 || (n > 0 && (!feature_vectors || !world_points || !solutions || !status))) return MPE_E_INVALID;
+  if (n == 0) return MPE_OK;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  double *df = nullptr, *dP = nullptr, *ds = nullptr;
+  int* dst = nullptr;
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, cudaMalloc((void**)&df, (size_t)n * 9 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc((void**)&dP, (size_t)n * 9 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc((void**)&ds, (size_t)n * 48 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc((void**)&dst, (size_t)n * sizeof(int)));
+  CUDA_TRY(c, cudaMemcpyAsync(df, feature_vectors, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(dP, world_points, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, launch_p3p_batch(df, dP, n, ds, dst, st));
+  ++c->launches;
+  CUDA_TRY(c, cudaMemcpyAsync(solutions, ds, (size_t)n * 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(status, dst, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  cudaFree(df); cudaFree(dP); cudaFree(ds); cudaFree(dst);
+  return MPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------- batch drivers
+int mpe_estimate_batch_device_async(mpe_ctx* c, const uint8_t* frames_device, int pitch, long long frame_stride, int width, int height, int n_frames) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!frames_device || n_frames < 1) return MPE_E_INVALID;
+  if (n_frames > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "batch or image larger than the context capacity");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  FrameSource src{frames_device, pitch, frame_stride, width, height, n_frames};
+  return run_cold(c, src, 0, n_frames, 0, c->stream);
+}
+
+int mpe_fetch_results(mpe_ctx* c, int n_frames, mpe_result* results) {
+  if (!c || !results || n_frames < 1 || n_frames > c->max_batch) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n_frames * sizeof(mpe_result), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(results, c->h_results, (size_t)n_frames * sizeof(mpe_result));
+  return MPE_OK;
+}
+
+int mpe_estimate_batch_device(mpe_ctx* c, const uint8_t* frames_device, int pitch, long long frame_stride, int width, int height, int n_frames, mpe_result* results) {
+  int rc = mpe_estimate_batch_device_async(c, frames_device, pitch, frame_stride, width, height, n_frames);
+  if (rc != MPE_OK) return rc;
+  return mpe_fetch_results(c, n_frames, results);
+}
+
+int mpe_estimate_batch(mpe_ctx* c, const uint8_t* frames, int pitch, long long frame_stride, int width, int height, int n_frames, mpe_result* results) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!frames || !results || n_frames < 1 || pitch < width) return MPE_E_INVALID;
+  if (width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "image larger than the context capacity");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const long long dev_stride = (long long)c->pitch * c->max_h;
+  FrameSource src{c->d.frames, c->pitch, dev_stride, width, height, c->max_batch};
+  // chunked pipeline: H2D of chunk i+1 (copy stream) overlaps the kernels of chunk i (compute stream)
+  int chunk = 128;
+  if (chunk > c->max_batch) chunk = c->max_batch;
+  for (int super = 0; super < n_frames; super += c->max_batch) {
+    int n_super = n_frames - super < c->max_batch ? n_frames - super : c->max_batch;
+    int n_chunks = (n_super + chunk - 1) / chunk;
+    while ((int)c->chunk_events.size() < n_chunks) {
+      cudaEvent_t e;
+      CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->chunk_events.push_back(e);
+    }
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      int f0 = ci * chunk;
+      int n = n_super - f0 < chunk ? n_super - f0 : chunk;
+      const uint8_t* hsrc = frames + (size_t)(super + f0) * frame_stride;
+      uint8_t* ddst = c->d.frames + (size_t)f0 * dev_stride;
+      if (pitch == c->pitch && frame_stride == dev_stride) {
+        CUDA_TRY(c, cudaMemcpyAsync(ddst, hsrc, (size_t)n * dev_stride, cudaMemcpyHostToDevice, c->copy_stream));
+      } else if (frame_stride == (long long)pitch * height && c->max_h == height) {
+        // frames are contiguous: one 2-D copy of n*height rows
+        CUDA_TRY(c, cudaMemcpy2DAsync(ddst, c->pitch, hsrc, pitch, width, (size_t)n * height, cudaMemcpyHostToDevice, c->copy_stream));
+      } else {
+        for (int f = 0; f < n; ++f)
+          CUDA_TRY(c, cudaMemcpy2DAsync(ddst + (size_t)f * dev_stride, c->pitch, hsrc + (size_t)f * frame_stride, pitch, width, height,
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      CUDA_TRY(c, cudaEventRecord(c->chunk_events[ci], c->copy_stream));
+      CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->chunk_events[ci], 0));
+      rc = run_cold(c, src, f0, n, f0, c->stream);
+      if (rc != MPE_OK) return rc;
+      CUDA_TRY(c, cudaMemcpyAsync(c->h_results + f0, c->d.results + f0, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(results + super, c->h_results, (size_t)n_super * sizeof(mpe_result));
+  }
+  return MPE_OK;
+}
+
+int mpe_copy_poses_device(mpe_ctx* c, int n_frames, double* poses_device) {
+  if (!c || !poses_device || n_frames < 1 || n_frames > c->max_batch) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpyAsync(poses_device, c->d.pose, (size_t)n_frames * 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return MPE_OK;
+}
+
+int mpe_streams_reset(mpe_ctx* c, int n_streams) {
+  (void)n_streams;
+  return fail(c, MPE_E_UNSUPPORTED, "device-side tracking loop not built yet");
+}
+int mpe_streams_step_device(mpe_ctx* c, const uint8_t*, int, long long, int, int, int, const double*, mpe_result*) {
+  return fail(c, MPE_E_UNSUPPORTED, "device-side tracking loop not built yet");
+}
+
+int mpe_enable_kernel_timing(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->timing = on != 0; return MPE_OK; }
+
+int mpe_get_kernel_times(mpe_ctx* c, float ms_out[4]) {
+  if (!c || !ms_out) return MPE_E_INVALID;
+  if (!c->timing || !c->timing_pending) return fail(c, MPE_E_INVALID, "kernel timing not enabled or no batch run yet");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  for (int k = 0; k < 4; ++k) {
+    CUDA_TRY(c, cudaEventSynchronize(c->ev[2 * k + 1]));
+    CUDA_TRY(c, cudaEventElapsedTime(&ms_out[k], c->ev[2 * k], c->ev[2 * k + 1]));
+  }
+  return MPE_OK;
+}
+
+long long mpe_kernel_launch_count(const mpe_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

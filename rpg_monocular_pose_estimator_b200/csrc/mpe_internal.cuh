@@ -1,0 +1,119 @@
+// Internal declarations shared by the kernels and the C-ABI implementation (not installed).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mpe_b200.h"
+
+namespace mpe {
+
+constexpr int kTileRows = 32;        // output rows per K1 tile (= bits of one row-flag word)
+constexpr int kMaxRadius = 4;        // largest Gaussian radius the fused kernel is instantiated for
+constexpr int kMaxTaps = 2 * kMaxRadius + 1;
+constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
+constexpr int kK1Threads = 256;
+constexpr int kCandCap = 256;        // candidate contour starts buffered per frame-warp in K1b
+
+// Camera model as the kernels consume it.
+struct DevCamera {
+  double K[9];                 // row-major camera_matrix_K_
+  double D[MPE_MAX_DIST];      // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 (zero padded)
+  int nD;
+};
+
+struct DevBlobParams {
+  double min_blob_area, max_blob_area, max_width_height_distortion, max_circular_distortion;
+};
+
+struct DevPoseParams {
+  double back_projection_pixel_tolerance;
+  double nearest_neighbour_pixel_tolerance;
+  double certainty_threshold;
+  double valid_correspondence_threshold;
+  uint32_t histogram_threshold;
+  int n_obj;
+  double markers[3 * MPE_MAX_LEDS];
+};
+
+struct Roi { int x, y, w, h; };   // same layout as mpe_rect / cv::Rect
+
+// Geometry of one K1 launch (uniform over the batch unless `rois` is given).
+struct K1Geom {
+  int n_frames;
+  int img_w, img_h;          // full frame size in pixels
+  Roi roi;                   // used when rois == nullptr
+  const Roi* rois;           // optional per-frame ROI (device)
+  int max_roi_w, max_roi_h;  // bounds for tile enumeration
+  int n_strips, n_ct;        // tiles per frame = n_strips * n_ct
+  int tw_px;                 // column-tile width in pixels (multiple of 32 when n_ct > 1)
+  int box_w;                 // TMA box inner extent in u32 elements (multiple of 4)
+  int mask_wpr;              // u32 words per mask row
+  int mask_rows;             // rows reserved per frame in the mask buffer
+  int flags_per_frame;       // row-flag words reserved per frame
+};
+
+struct K1aArgs {
+  K1Geom g;
+  int thr_k;                 // SWAR constant for "any byte > threshold"
+  int threshold;
+  uint32_t taps[kMaxTaps];   // 8.8 fixed-point Gaussian taps, sum = 256
+  uint32_t* rowflags;        // [n_frames][flags_per_frame]
+  uint32_t* mask;            // [n_frames][mask_rows][mask_wpr]
+};
+
+struct K1bArgs {
+  K1Geom g;
+  const uint32_t* rowflags;
+  const uint32_t* mask;
+  DevCamera cam;
+  DevBlobParams bp;
+  // outputs
+  int* n_det;                // [n_frames]
+  int* flags;                // [n_frames]
+  double* det;               // [n_frames][MPE_MAX_BLOBS][2] undistorted
+  float* centers;            // [n_frames][MPE_MAX_BLOBS][2] distorted
+};
+
+struct K2Args {
+  int n_frames;
+  const int* n_det;          // [n_frames]
+  const double* det;         // [n_frames][det_stride][2]
+  int det_stride;            // points reserved per frame in det
+  DevCamera cam;
+  DevPoseParams pp;
+  int split;                 // CTAs per frame
+  uint32_t* hist;            // [n_frames][MPE_MAX_DET*MPE_MAX_LEDS], zeroed before launch
+  uint32_t* done_counter;    // [n_frames], zeroed before launch
+  uint32_t* corr;            // [n_frames][2*MPE_MAX_LEDS]
+  int* n_corr;               // [n_frames]
+  int* frame_flags;          // [n_frames] in/out
+  const uint8_t* active;     // optional [n_frames]: run the sweep only where nonzero
+};
+
+struct K3Args {
+  int n_frames;
+  const int* n_det;
+  const double* det;
+  int det_stride;
+  DevCamera cam;
+  DevPoseParams pp;
+  const uint32_t* corr;      // [n_frames][2*MPE_MAX_LEDS]
+  const int* n_corr;         // [n_frames]
+  int mode;                  // 0: check + GN (cold path), 1: check only, 2: GN only (pose_io is the start)
+  double* pose_io;           // [n_frames][16] row-major
+  double* cov;               // [n_frames][36]
+  int* ok;                   // [n_frames] checkCorrespondences result
+  int* iters;                // [n_frames]
+  int* updated;              // [n_frames]
+  const uint8_t* active;     // optional
+};
+
+// ---- launchers (defined next to the kernels) ----
+cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
+cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);
+cudaError_t launch_p3p_sweep(const K2Args& a, cudaStream_t st);
+cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st);
+cudaError_t launch_p3p_batch(const double* f, const double* P, int n, double* sol, int* status, cudaStream_t st);
+size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages);
+
+}  // namespace mpe

@@ -1,0 +1,116 @@
+"""K1 parity: mpe_find_leds (CUDA) against the cv2 oracle of LEDDetector::findLeds — bit exact:
+same number of detections, same order, identical float32 centres and identical undistorted positions."""
+import numpy as np
+import pytest
+
+from rpg_monocular_pose_estimator_b200 import synth
+from tests.helpers import oracle_find_leds, random_blob_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(ctx, img, roi, params, K, D, tag=""):
+    ctx.set_camera(K, D)
+    ctx.set_params(params)
+    px, centers, flags = ctx.find_leds(img, roi)
+    opx, ocenters = oracle_find_leds(img, roi, params, K, D)
+    assert flags == 0, f"{tag}: flags {flags}"
+    assert len(centers) == len(ocenters), f"{tag}: n_det gpu {len(centers)} oracle {len(ocenters)}"
+    if len(ocenters):
+        assert np.array_equal(centers.view(np.uint32), ocenters.view(np.uint32)), f"{tag}: centres differ\n{centers}\n{ocenters}"
+        assert np.array_equal(px, opx), f"{tag}: undistorted positions differ\n{px - opx}"
+    return len(ocenters)
+
+
+def test_synthetic_led_frames_full_image(gpu_ctx_752):
+    for n_leds in (4, 5, 8):
+        sc = synth.make_cold_scene(6, n_leds=n_leds, seed=1000 + n_leds)
+        for f in range(6):
+            n = _compare(gpu_ctx_752, sc.frames[f], (0, 0, sc.width, sc.height), sc.params, sc.K, sc.D, f"leds{n_leds} f{f}")
+            assert n == n_leds
+
+
+@pytest.mark.parametrize("kind", ["ellipse", "mixed"])
+def test_random_blobs_full_image(gpu_ctx_752, kind):
+    rng = np.random.default_rng(7)
+    K, D = synth.camera()
+    total = 0
+    for it in range(40):
+        img = random_blob_image(rng, 480, 752, n_blobs=int(rng.integers(1, 25)), kind=kind)
+        p = synth.Params(threshold_value=int(rng.choice([100, 127, 128, 140, 200])), min_blob_area=float(rng.choice([0.5, 10, 30])),
+                         max_blob_area=float(rng.choice([200, 1000])), max_width_height_distortion=float(rng.choice([0.5, 0.9])),
+                         max_circular_distortion=float(rng.choice([0.5, 0.95])))
+        total += _compare(gpu_ctx_752, img, (0, 0, 752, 480), p, K, D, f"{kind} it{it}")
+    assert total > 50
+
+
+def test_roi_subrects_and_border_blobs(gpu_ctx_752):
+    rng = np.random.default_rng(11)
+    K, D = synth.camera()
+    p = synth.Params(min_blob_area=1.0, max_blob_area=2000, max_width_height_distortion=0.95, max_circular_distortion=0.99)
+    total = 0
+    for it in range(60):
+        img = random_blob_image(rng, 480, 752, n_blobs=30, kind="mixed")
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        if it % 10 == 0:
+            w, h = int(rng.integers(1, 6)), int(rng.integers(1, 6))       # tiny ROIs: reflect bounces
+        x, y = int(rng.integers(0, 752 - w + 1)), int(rng.integers(0, 480 - h + 1))
+        total += _compare(gpu_ctx_752, img, (x, y, w, h), p, K, D, f"roi it{it} {(x, y, w, h)}")
+    assert total > 30
+
+
+@pytest.mark.parametrize("sigma", [0.3, 0.45, 0.6, 0.8, 1.0, 1.2, 1.4])
+def test_other_sigmas(gpu_ctx_752, sigma):
+    rng = np.random.default_rng(int(sigma * 100))
+    K, D = synth.camera()
+    p = synth.Params(gaussian_sigma=sigma, min_blob_area=1.0, max_blob_area=3000, max_width_height_distortion=0.95,
+                     max_circular_distortion=0.99)
+    for it in range(6):
+        img = random_blob_image(rng, 480, 752, n_blobs=12, kind="mixed")
+        roi = (0, 0, 752, 480) if it % 2 == 0 else (100, 50, 333, 217)
+        _compare(gpu_ctx_752, img, roi, p, K, D, f"sigma{sigma} it{it}")
+
+
+def test_thresholds_and_bright_background(gpu_ctx_752):
+    rng = np.random.default_rng(3)
+    K, D = synth.camera()
+    for thr in (0, 1, 50, 127, 128, 129, 254, 255):
+        img = random_blob_image(rng, 480, 752, n_blobs=10, kind="mixed", noise_max=int(rng.choice([20, 100, 200])))
+        p = synth.Params(threshold_value=thr, min_blob_area=1.0, max_blob_area=1e9, max_width_height_distortion=1.0,
+                         max_circular_distortion=1.0)
+        # a bright background makes one huge component: check it does not break (area filter open)
+        if thr < 100:
+            img = img[:96, :128].copy()
+            import rpg_monocular_pose_estimator_b200 as mpe
+        _compare(gpu_ctx_752, img, (0, 0, img.shape[1], img.shape[0]), p, K, D, f"thr{thr}")
+
+
+def test_empty_and_saturated(gpu_ctx_752):
+    K, D = synth.camera()
+    p = synth.Params()
+    img = np.zeros((480, 752), np.uint8)
+    assert _compare(gpu_ctx_752, img, (0, 0, 752, 480), p, K, D, "black") == 0
+    img[:] = 255
+    _compare(gpu_ctx_752, img, (0, 0, 752, 480), p, K, D, "white")
+    _compare(gpu_ctx_752, img, (10, 10, 40, 40), synth.Params(max_blob_area=1e6, max_circular_distortion=1.0), K, D, "white roi")
+
+
+def test_1080p_two_column_tiles():
+    import rpg_monocular_pose_estimator_b200 as mpe
+    ctx = mpe.Context(0, 2, 1920, 1080)
+    try:
+        K, D = synth.camera(1920, 1080)
+        sc = synth.make_cold_scene(3, n_leds=5, width=1920, height=1080, seed=77)
+        for f in range(3):
+            assert _compare(ctx, sc.frames[f], (0, 0, 1920, 1080), sc.params, sc.K, sc.D, f"1080p f{f}") == 5
+        rng = np.random.default_rng(5)
+        p = synth.Params(min_blob_area=1.0, max_blob_area=5000, max_width_height_distortion=0.95, max_circular_distortion=0.99)
+        for it in range(6):
+            img = random_blob_image(rng, 1080, 1920, n_blobs=60, kind="mixed")
+            # blobs straddling the column-tile seam at x = 960
+            for yy in range(50, 1000, 90):
+                img[yy:yy + 9, 955:966] = 250
+            roi = (0, 0, 1920, 1080) if it % 2 == 0 else (17, 33, 1800, 900)
+            _compare(ctx, img, roi, p, K, D, f"1080p random it{it}")
+    finally:
+        ctx.close()

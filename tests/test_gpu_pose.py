@@ -1,0 +1,165 @@
+"""K2/K3 parity against the C++ oracle of the pose path (oracle/pose_oracle.cpp).
+Integer results (histogram, correspondences, iteration counts) must be identical; P3P solutions to 1e-9
+relative; poses within 1e-6 m / 1e-6 rad (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from rpg_monocular_pose_estimator_b200 import synth
+from oracle import pose_oracle
+from tests.helpers import oracle_find_leds, pose_error
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-6   # metres  (BASELINE.json north_star)
+ROT_TOL = 1e-6   # radians
+
+
+def _detections(sc, f):
+    px, _ = oracle_find_leds(sc.frames[f], (0, 0, sc.width, sc.height), sc.params, sc.K, sc.D)
+    return px
+
+
+def _config(ctx, sc):
+    ctx.set_camera(sc.K, sc.D)
+    ctx.set_params(sc.params)
+    ctx.set_markers(sc.markers)
+
+
+def test_p3p_random_problems(gpu_ctx_752):
+    rng = np.random.default_rng(0)
+    n = 4000
+    F = np.zeros((n, 3, 3)); P = np.zeros((n, 3, 3))
+    for i in range(n):
+        pts = rng.uniform(-0.2, 0.2, size=(3, 3))                       # rows = points
+        if i % 50 == 0:
+            pts[2] = pts[0] + 2.0 * (pts[1] - pts[0])                   # colinear -> -1
+        Rm = synth.rodrigues(rng.normal(size=3) * 0.8)
+        t = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(0.4, 1.5)])
+        cam = (Rm @ pts.T).T + t
+        f = cam / np.linalg.norm(cam, axis=1, keepdims=True)
+        if i % 7 == 0:
+            f += rng.normal(size=f.shape) * 0.05                         # inconsistent bearings: complex roots / NaNs
+            f /= np.linalg.norm(f, axis=1, keepdims=True)
+        F[i] = f.T; P[i] = pts.T                                          # columns
+    st, sol = gpu_ctx_752.p3p(F, P)
+    n_nan_mismatch = 0; worst = 0.0
+    for i in range(n):
+        rc, osol = pose_oracle.p3p(F[i], P[i])
+        assert rc == st[i]
+        if rc != 0:
+            continue
+        a, b = sol[i], osol
+        fa, fb = np.isfinite(a), np.isfinite(b)
+        if not np.array_equal(fa, fb):
+            n_nan_mismatch += 1
+            continue
+        m = fa
+        if m.any():
+            err = np.abs(a[m] - b[m]) / np.maximum(1.0, np.abs(b[m]))
+            worst = max(worst, float(err.max()))
+    assert n_nan_mismatch == 0
+    assert worst < 1e-7, worst       # ill-conditioned (near-double-root) cases amplify 1-ulp libm differences
+
+
+@pytest.mark.parametrize("n_leds", [4, 5, 8])
+def test_initialise_histogram_and_correspondences_exact(gpu_ctx_752, n_leds):
+    sc = synth.make_cold_scene(10 if n_leds < 8 else 4, n_leds=n_leds, seed=200 + n_leds)
+    _config(gpu_ctx_752, sc)
+    for f in range(len(sc.frames)):
+        det = _detections(sc, f)
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        est.set_image_points(det)
+        ok_o = est.initialise()
+        ok, hist, corr, pose = gpu_ctx_752.initialise(det)
+        assert np.array_equal(hist, est.histogram()), f"frame {f} histogram differs\n{hist}\n{est.histogram()}"
+        assert np.array_equal(corr, est.correspondences()), f"frame {f}"
+        assert ok == ok_o
+        if ok:
+            dt, dr = pose_error(pose, est.predicted_pose())
+            assert dt < POS_TOL and dr < ROT_TOL, (dt, dr)
+
+
+def test_check_and_optimise_stage_calls(gpu_ctx_752):
+    sc = synth.make_cold_scene(8, n_leds=5, seed=321)
+    _config(gpu_ctx_752, sc)
+    for f in range(8):
+        det = _detections(sc, f)
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        est.set_image_points(det)
+        assert est.initialise() == 1
+        corr = est.correspondences()
+        T0 = est.predicted_pose()
+        ok, pose = gpu_ctx_752.check_correspondences(det, corr)
+        assert ok == 1
+        dt, dr = pose_error(pose, T0)
+        assert dt < POS_TOL and dr < ROT_TOL
+        it_o = est.optimise_pose()
+        pose2, cov, it = gpu_ctx_752.optimise_pose(det, corr, T0)
+        dt, dr = pose_error(pose2, est.predicted_pose())
+        assert dt < POS_TOL and dr < ROT_TOL, (dt, dr)
+        assert it == it_o, (it, it_o)
+        co = est.covariance()
+        assert np.allclose(cov, co, rtol=1e-6, atol=1e-12 * np.abs(co).max())
+        # wrong correspondences must be rejected by both
+        bad = corr.copy(); bad[:, 1] = np.roll(bad[:, 1], 1)
+        est.set_correspondences(bad)
+        assert gpu_ctx_752.check_correspondences(det, bad)[0] == est.check_correspondences()
+
+
+@pytest.mark.parametrize("n_leds,n_frames", [(4, 16), (5, 48), (8, 6)])
+def test_cold_batch_matches_oracle(gpu_ctx_752, n_leds, n_frames):
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    sc = synth.make_cold_scene(n_frames, n_leds=n_leds, seed=5000 + n_leds)
+    _config(gpu_ctx_752, sc)
+    res = results_to_arrays(gpu_ctx_752.estimate_batch(sc.frames))
+    n_upd = 0; iter_mismatch = 0
+    for f in range(n_frames):
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        upd = est.estimate_body_pose(sc.frames[f], sc.times[f])
+        r = res[f]
+        assert bool(r["updated"]) == upd, f
+        assert r["n_det"] == est.n_det
+        if upd:
+            n_upd += 1
+            k = r["n_corr"]
+            assert np.array_equal(r["corr"][:2 * k].reshape(k, 2), est.correspondences()), f
+            dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+            assert dt < POS_TOL and dr < ROT_TOL, (f, dt, dr)
+            iter_mismatch += int(r["gn_iters"] != est.gn_iterations())
+            co = est.covariance()
+            assert np.allclose(r["cov"].reshape(6, 6), co, rtol=1e-6, atol=1e-12 * np.abs(co).max())
+    assert n_upd == n_frames
+    assert iter_mismatch == 0
+
+
+def test_pose_estimator_tracking_sequence(gpu_ctx_752):
+    """estimateBodyPose over a stream: cold start, then ROI tracking (predictWithROI, findCorrespondences, check, GN)."""
+    import rpg_monocular_pose_estimator_b200 as mpe
+    sc = synth.make_stream_scene(25, n_leds=5, seed=9)
+    pe = mpe.PoseEstimator(gpu_ctx_752)
+    pe.configure(sc.K, sc.D, sc.markers, sc.params)
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    for f in range(25):
+        a = pe.estimateBodyPose(sc.frames[f], sc.times[f])
+        b = est.estimate_body_pose(sc.frames[f], sc.times[f])
+        assert a == b, f
+        assert tuple(pe.region_of_interest_) == tuple(est.region_of_interest), (f, pe.region_of_interest_, est.region_of_interest)
+        if b:
+            assert np.array_equal(pe.getCorrespondences(), est.correspondences()), f
+            dt, dr = pose_error(pe.getPredictedPose(), est.predicted_pose())
+            assert dt < POS_TOL and dr < ROT_TOL, (f, dt, dr)
+    assert pe.it_since_initialized_ == 2
+    assert pe.region_of_interest_[2] < 752     # really tracking inside an ROI
+
+
+def test_too_few_leds_is_not_an_error(gpu_ctx_752):
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    sc = synth.make_cold_scene(2, n_leds=5, seed=1)
+    _config(gpu_ctx_752, sc)
+    frames = sc.frames.copy()
+    frames[0][:, :376] = 0            # wipe half the image: fewer than 4 LEDs are likely left
+    frames[1][:] = 0
+    res = results_to_arrays(gpu_ctx_752.estimate_batch(frames))
+    assert res[1]["updated"] == 0 and res[1]["n_det"] == 0
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    assert bool(res[0]["updated"]) == est.estimate_body_pose(frames[0], 0.0)
