@@ -212,7 +212,8 @@ def main():
     ctx.set_camera(scene.K, scene.D)
     ctx.set_params(scene.params)
     ctx.set_markers(scene.markers)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # explicit stream: events and kernels share it (handle 0 would mean "own stream")
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.enable_kernel_timing(True)
     rec_bytes = C.sizeof(mpe.MpeResult)

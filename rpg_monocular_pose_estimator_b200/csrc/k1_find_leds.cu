@@ -87,7 +87,10 @@ __device__ __forceinline__ uint32_t any_byte_gt(uint32_t w, uint32_t k) {
   return (kLow ? (x | w) : (x & w)) & 0x80808080u;
 }
 
-__device__ __forceinline__ int floor_div4(int v) { return v >> 2; }   // arithmetic shift = floor for negatives
+// TMA requires the innermost start coordinate to be a multiple of 16 bytes (measured on B200: any other value raises
+// 'illegal instruction', tests/probes/tma_probe.cu), so tiles start at a 16-pixel boundary: first u32 element of the
+// 16-pixel group that contains pixel v (arithmetic shift = floor for negatives).
+__device__ __forceinline__ int tile_elem0(int v) { return (v >> 4) << 2; }
 
 struct TileCoord {
   int f, s, ct;
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
   const int row_bytes = box_w * 4;
   const int hot_wpr = (box_w + 31) >> 5;
   const int om_wpr = (g.tw_px + 31) >> 5;
-  const uint32_t stage_bytes = (uint32_t)(kRows * row_bytes);
+  const uint32_t stage_bytes = (uint32_t)(kRows * row_bytes);          // bytes one TMA box delivers
+  const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;           // TMA destinations must be 128-byte aligned
 
   K1Smem sm;
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -169,10 +173,10 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
       ptile += gridDim.x;
       if (!c.valid) continue;
       int stage = pcount % kStages;
-      int x_elem0 = floor_div4(c.roi.x + c.ct * g.tw_px - R);
+      int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
       int y0 = c.roi.y + c.s * kTileRows - R;
       mbar_expect_tx(&sm.bars[stage], stage_bytes);
-      tma_load_3d(sm.ring + (size_t)stage * stage_bytes, &tmap, &sm.bars[stage], x_elem0, y0, c.f);
+      tma_load_3d(sm.ring + (size_t)stage * stage_stride, &tmap, &sm.bars[stage], x_elem0, y0, c.f);
       ++pcount;
       return;
     }
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
     const uint32_t parity = (uint32_t)((ccount / kStages) & 1);
     ++ccount;
     mbar_wait(&sm.bars[stage], parity);
-    const uint8_t* tile_smem = sm.ring + (size_t)stage * stage_bytes;
+    const uint8_t* tile_smem = sm.ring + (size_t)stage * stage_stride;
 
     // ---------------- dense phase: is anything above the threshold in this tile? ----------------
     uint32_t local_hot = 0;
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
     }
     int any_hot = __syncthreads_or((int)local_hot);
 
-    const int x_elem0 = floor_div4(c.roi.x + c.ct * g.tw_px - R);
+    const int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
     const int y0 = c.roi.y + c.s * kTileRows - R;
     const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
     uint32_t* flag_ptr = a.rowflags + (size_t)c.f * g.flags_per_frame + c.s * g.n_ct + c.ct;
@@ -326,7 +330,8 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
 
 size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages) {
   int rows = kTileRows + 2 * radius;
-  return k1_ring_offset(rows, g.box_w, g.tw_px) + (size_t)stages * rows * g.box_w * 4;
+  size_t stage_stride = ((size_t)rows * g.box_w * 4 + 127) & ~(size_t)127;
+  return k1_ring_offset(rows, g.box_w, g.tw_px) + (size_t)stages * stage_stride;
 }
 
 template <int R, bool kLow, int kStages>

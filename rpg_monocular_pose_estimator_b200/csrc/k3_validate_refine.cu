@@ -14,6 +14,7 @@
 // Latency bound (a dependent chain of ~5 iterations); reads < 1 KB per frame.  Compiled with -fmad=false.
 #include "mpe_internal.cuh"
 #include "p3p_device.cuh"
+#include <cstdio>
 
 namespace mpe {
 
@@ -110,51 +111,115 @@ __device__ void svd3(const double Ain[3][3], double U[3][3], double V[3][3]) {
   }
 }
 
-// Symmetric solve by LDL^T with diagonal pivoting; same operation order as oracle ldlt_solve6.
-__device__ void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) {
-  double A[6][6];
-  int perm[6];
-  for (int i = 0; i < 6; ++i) { perm[i] = i; for (int j = 0; j < 6; ++j) A[i][j] = Ain[i * 6 + j]; }
+// Symmetric solve by LDL^T with diagonal pivoting; same arithmetic, in the same order, as oracle ldlt_solve6.
+// Written with compile-time indices only (the pivot exchange is a predicated swap over the unrolled candidates), so
+// the 6x6 system stays in registers.  NB: the first version indexed local arrays with the run-time pivot; nvcc 12.9
+// (-O3, sm_100a) miscompiled it inside this kernel (wrong solution, fixed by -Xcicc -O1) — see DESIGN.md, "toolchain".
+__device__ __forceinline__ void swap_d(double& a, double& b) { double t = a; a = b; b = t; }
+
+__device__ __forceinline__ void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) {
+  double A[6][6], y[6];
+  int piv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    y[i] = bin[i];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[i][j] = Ain[i * 6 + j];
+  }
+#pragma unroll
   for (int k = 0; k < 6; ++k) {
     int p = k;
     double best = fabs(A[k][k]);
-    for (int i = k + 1; i < 6; ++i) if (fabs(A[i][i]) > best) { best = fabs(A[i][i]); p = i; }
-    if (p != k) {
-      for (int j = 0; j < 6; ++j) { double t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
-      for (int i = 0; i < 6; ++i) { double t = A[i][k]; A[i][k] = A[i][p]; A[i][p] = t; }
-      int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      double v = fabs(A[i][i]);
+      if (v > best) { best = v; p = i; }
+    }
+    piv[k] = p;
+#pragma unroll
+    for (int q = k + 1; q < 6; ++q) {
+      if (p == q) {   // symmetric exchange of rows/columns k and q, right-hand side follows
+#pragma unroll
+        for (int j = 0; j < 6; ++j) swap_d(A[k][j], A[q][j]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) swap_d(A[i][k], A[i][q]);
+        swap_d(y[k], y[q]);
+      }
     }
     double d = A[k][k];
+#pragma unroll
     for (int i = k + 1; i < 6; ++i)
+#pragma unroll
       for (int j = k + 1; j <= i; ++j) A[i][j] -= A[i][k] * A[j][k] / d;
+#pragma unroll
     for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
-    for (int i = k + 1; i < 6; ++i) for (int j = k + 1; j < i; ++j) A[j][i] = A[i][j];
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+      for (int j = k + 1; j < i; ++j) A[j][i] = A[i][j];
   }
-  double y[6];
-  for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
   for (int i = 0; i < 6; ++i) y[i] /= A[i][i];
-  for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+  // undo the exchanges (x = P^T y): transpositions in reverse order
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+#pragma unroll
+    for (int q = k + 1; q < 6; ++q)
+      if (piv[k] == q) swap_d(y[k], y[q]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
-// General 6x6 inverse (Gauss-Jordan, partial pivoting); same operation order as oracle inverse6.
-__device__ void inverse6(const double Ain[36], double out[36]) {
+// General 6x6 inverse (Gauss-Jordan, partial pivoting); same arithmetic as oracle inverse6, compile-time indices.
+__device__ __forceinline__ void inverse6(const double Ain[36], double out[36]) {
   double a[6][12];
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { a[i][j] = Ain[i * 6 + j]; a[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { a[i][j] = Ain[i * 6 + j]; a[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
   for (int k = 0; k < 6; ++k) {
     int p = k;
     double best = fabs(a[k][k]);
-    for (int i = k + 1; i < 6; ++i) if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); p = i; }
-    if (p != k) for (int j = 0; j < 12; ++j) { double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
-    double piv = a[k][k];
-    for (int j = 0; j < 12; ++j) a[k][j] /= piv;
-    for (int i = 0; i < 6; ++i) if (i != k) {
-      double fct = a[i][k];
-      if (fct != 0) for (int j = 0; j < 12; ++j) a[i][j] -= fct * a[k][j];
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      double v = fabs(a[i][k]);
+      if (v > best) { best = v; p = i; }
+    }
+#pragma unroll
+    for (int q = k + 1; q < 6; ++q) {
+      if (p == q) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) swap_d(a[k][j], a[q][j]);
+      }
+    }
+    double pv = a[k][k];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a[k][j] /= pv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i != k) {
+        double fct = a[i][k];
+        if (fct != 0) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) a[i][j] -= fct * a[k][j];
+        }
+      }
     }
   }
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[i * 6 + j] = a[i][6 + j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[i * 6 + j] = a[i][6 + j];
 }
 
 // pose_estimator.cpp:962-994; T (3x4 row-major top rows) <- exp(twist) * T
@@ -416,6 +481,13 @@ __global__ void __launch_bounds__(32 * kK3WarpsPerCta) validate_refine_kernel(co
       ++iters;
       double mx = -1;                                                   // norm_max :1073-1085
       for (int q = 0; q < 6; ++q) { double av = fabs(dT[q]); if (av > mx) mx = av; }
+#ifdef MPE_DEBUG_GN
+      if (lane == 0 && f == 0 && iters == 1) {
+        for (int r = 0; r < 6; ++r) printf("A[%d] %.9e %.9e %.9e %.9e %.9e %.9e | b %.9e\n", r, A[r*6], A[r*6+1], A[r*6+2], A[r*6+3], A[r*6+4], A[r*6+5], b[r]);
+        printf("amask %x k %d\n", amask, k);
+      }
+      if (lane == 0 && f == 0) printf("GN it %d mx %.3e dT %.3e %.3e %.3e %.3e %.3e %.3e | A00 %.6e A55 %.6e b0 %.3e T3 %.9f %.9f %.9f\n", iters, mx, dT[0], dT[1], dT[2], dT[3], dT[4], dT[5], A[0], A[35], b[0], T[3], T[7], T[11]);
+#endif
       if (mx <= 1e-13) break;                                           // :786
     }
     inverse6(A, cov);                                                   // :790

@@ -133,8 +133,9 @@ int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_
   g->n_ct = (max_roi_w + tw - 1) / tw;
   if (g->n_ct > 1) tw = kMaxTileWidthPx;
   g->tw_px = tw;
-  // widest span of u32 elements a tile can touch: [floor((x - R)/4), floor((x + tw + R - 1)/4)] for any x
-  int span = (tw + 2 * radius + 3 + 3) / 4 + 1;
+  // widest span of u32 elements a tile can touch: it starts at the 16-pixel boundary at or below x - R (TMA needs a
+  // 16-byte aligned innermost coordinate) and must reach pixel x + tw + R - 1
+  int span = (tw + 2 * radius - 1 + 15) / 4 + 1;
   g->box_w = (span + 3) & ~3;
   if (g->box_w > 256) return MPE_E_UNSUPPORTED;
   g->mask_wpr = c->mask_wpr;
