@@ -54,7 +54,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -63,6 +63,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -83,6 +84,8 @@ class ClockSampler:
             for n, v in zip(names, parts[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        if not sm:
+            out["error"] = "no nvidia-smi samples"
         if sm:
             out["sm_mhz"] = statistics.median(sm)
             out["sm_max_mhz"] = max(mx)
@@ -244,12 +247,11 @@ def main():
             if upd:
                 assert np.abs(res[f]["pose"].reshape(4, 4) - est.predicted_pose()).max() < 1e-6, "GPU/oracle pose mismatch"
 
-    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # sampled from the warm-up on: the timed region alone can be shorter than one sample period
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches1 = ctx.launch_count()
     e0.record(stream)

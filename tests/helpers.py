@@ -36,5 +36,9 @@ def pose_error(Ta, Tb):
     """translation error (m), rotation error (rad)"""
     dt = float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
     R = Ta[:3, :3].T @ Tb[:3, :3]
-    c = max(-1.0, min(1.0, (np.trace(R) - 1) / 2))
-    return dt, float(np.arccos(c))
+    if not np.all(np.isfinite(R)):
+        return float("nan"), float("nan")
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = float(np.linalg.norm(w))                       # sin(angle): accurate for small angles (arccos of the trace is not)
+    c = (np.trace(R) - 1) / 2
+    return dt, float(np.arctan2(s, c))
