@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) p3p_sweep_kernel(const K2Args a
   const int n_comb = n_det * (n_det - 1) * (n_det - 2) / 6;
   const int n_perm = n_obj * (n_obj - 1) * (n_obj - 2);
   const int total = n_comb * n_perm;
-  const double tol = a.pp.back_projection_pixel_tolerance;
+  const double tol_sq_max = a.pp.back_proj_sq_max;
   const int n_unused_obj = n_obj - 3;
 
   for (int t = part * kK2Threads + tid; t < total; t += a.split * kK2Threads) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) p3p_sweep_kernel(const K2Args a
 
     for (int k = 0; k < 4; ++k) {
       double H[12];
-      p3p_solution(S, k, H);
+      if (!p3p_solution(S, k, H)) continue;
       if (!h_is_finite(H)) continue;                       // pose_estimator.cpp:653
       double Hi[12], KT[12];
       h_inverse(H, Hi);                                    // :660
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) p3p_sweep_kernel(const K2Args a
           double d2v = dx * dx + dy * dy;
           if (d2v < best) { best = d2v; bj = j; }
         }
-        if (sqrt(best) < tol) within |= 1u << ui;           // :671 strict <
+        if (best <= tol_sq_max) within |= 1u << ui;        // :671  sqrt(best) < tol, see DevPoseParams::back_proj_sq_max
         pairs |= (unsigned long long)bj << (4 * ui);
         ++ui;
       }
@@ -251,7 +251,9 @@ __global__ void p3p_batch_kernel(const double* __restrict__ f, const double* __r
   }
   for (int k = 0; k < 4; ++k) {
     double H[12];
-    p3p_solution(S, k, H);
+    if (!p3p_solution(S, k, H)) {
+      for (int e = 0; e < 12; ++e) H[e] = nan("");          // what the full evaluation yields: NaN in every entry of R (C may differ)
+    }
     for (int e = 0; e < 12; ++e) out[12 * k + e] = H[e];
   }
 }

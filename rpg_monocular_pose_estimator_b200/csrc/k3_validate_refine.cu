@@ -3,22 +3,22 @@
 // followed by PoseEstimator::optimisePose (:733-792: Gauss-Newton on SE(3) with computeJacobian :932-960,
 // exponentialMap :962-994, A.ldlt().solve(b), covariance = A^-1 of the last iteration).
 //
-// Mapping: one WARP per frame.
-//   check   lane <-> one 3-subset of the correspondence rows (P3P + greedy matching of the unused rows);
-//           contributions to the mean re-projected object points are summed in subset order (lane order),
-//           so the floating-point result does not depend on the warp schedule;
-//   GN      lane <-> one correspondence: residual, 2x6 Jacobian, J^T J (21 unique entries) and J^T e are
-//           formed per lane and accumulated in correspondence order through shuffles into registers that
-//           every lane holds; the 6x6 pivoted LDL^T solve and the exponential map are then evaluated
-//           redundantly by all lanes (no broadcast, no divergence).
-// Latency bound (a dependent chain of ~5 iterations); reads < 1 KB per frame.  Compiled with -fmad=false.
+// Mapping (throughput first: thousands of frames per launch, so the parallel axis is the FRAME, not the lane):
+//   check_kernel   one thread per (frame, 3-subset of the correspondence rows): P3P + greedy matching of the unused
+//                  rows; the subsets' contributions to the mean re-projected object points go through shared memory
+//                  and are summed by one thread per frame in subset order (= the reference's loop order), so the
+//                  floating-point result is schedule independent;
+//   refine_kernel  one thread per frame: acceptance test, Kabsch (3x3 Jacobi SVD), then Gauss-Newton with every
+//                  accumulation in correspondence order, pivoted LDL^T, exponential map, covariance = A^-1.
+// (The first version used one warp per frame with lanes = subsets / correspondences and shuffle reductions; 31/32 of
+//  the issue slots of the sequential parts were wasted: 150 ns/frame against ~15 for this layout.)
+// FP64 / latency bound; reads < 1 KB per frame.  Compiled with -fmad=false.
 #include "mpe_internal.cuh"
 #include "p3p_device.cuh"
 #include <cstdio>
 
 namespace mpe {
 
-constexpr int kK3WarpsPerCta = 4;
 constexpr int kMaxUnused = MPE_MAX_LEDS - 3;
 
 __device__ __forceinline__ void unrank_comb3_k3(int n, int idx, int& a, int& b, int& c) {
@@ -261,192 +261,250 @@ __device__ void exp_map_left_multiply(const double twist[6], double T[12]) {
   for (int e = 0; e < 12; ++e) T[e] = Tn[e];
 }
 
-struct K3Warp {
+// ------------------------------------------------------------------------------------------------
+// K3a — check_kernel: one THREAD per (frame, 3-subset of the correspondence rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int kK3aThreads = 128;
+
+struct CheckFrame {
   double det[MPE_MAX_DET][2];
   double bearing[MPE_MAX_DET][3];
   uint32_t corr[MPE_MAX_LEDS][2];
+  int k, N, valid;
 };
 
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__global__ void __launch_bounds__(kK3aThreads) check_kernel(const K3Args a, int G, int Nmax) {
+  extern __shared__ __align__(16) uint8_t k3_smem[];
+  const int n_obj = a.pp.n_obj;
+  CheckFrame* fr = reinterpret_cast<CheckFrame*>(k3_smem);
+  double* contrib = reinterpret_cast<double*>(k3_smem + (size_t)G * sizeof(CheckFrame));   // [kK3aThreads][n_obj*3]
+  int* found_s = reinterpret_cast<int*>(contrib + (size_t)kK3aThreads * n_obj * 3);       // [kK3aThreads]
+  const int tid = threadIdx.x;
+  const int f0 = blockIdx.x * G;
+  const double* K = a.cam.K;
+  const double* mk = a.pp.markers;
 
-__global__ void __launch_bounds__(32 * kK3WarpsPerCta) validate_refine_kernel(const K3Args a) {
-  __shared__ K3Warp shw[kK3WarpsPerCta];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * kK3WarpsPerCta + warp;
+  // ---- stage the frames of this CTA
+  if (tid < G) {
+    int f = f0 + tid;
+    int valid = (f < a.n_frames) && !(a.active && !a.active[f]);
+    int k = 0, n_det = 0;
+    if (valid) {
+      n_det = a.n_det[f];
+      k = a.n_corr[f];
+      if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;      // memory-safety guard
+      if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
+    }
+    fr[tid].valid = valid;
+    fr[tid].k = k;
+    fr[tid].N = (k >= 4) ? k * (k - 1) * (k - 2) / 6 : 0;                  // pose_estimator.cpp:401
+  }
+  for (int idx = tid; idx < G * MPE_MAX_DET; idx += kK3aThreads) {
+    int g = idx / MPE_MAX_DET, l = idx - g * MPE_MAX_DET;
+    int f = f0 + g;
+    if (f < a.n_frames) {
+      int n_det = a.n_det[f];
+      if (l < n_det && n_det <= MPE_MAX_DET) {
+        const double* det = a.det + (size_t)f * a.det_stride * 2;
+        double u = det[2 * l], v = det[2 * l + 1];
+        fr[g].det[l][0] = u; fr[g].det[l][1] = v;
+        double x = (u - K[2]) / K[0], y = (v - K[5]) / K[4], z = 1;       // calculateImageVectors :288-301
+        double n = sqrt(x * x + y * y + z * z);
+        fr[g].bearing[l][0] = x / n; fr[g].bearing[l][1] = y / n; fr[g].bearing[l][2] = z / n;
+      }
+      int k = a.n_corr[f];
+      if (l < k && l < MPE_MAX_LEDS) {
+        fr[g].corr[l][0] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * l];
+        fr[g].corr[l][1] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * l + 1];
+      }
+    }
+  }
+  __syncthreads();
+
+  const int g = (G > 1) ? tid / Nmax : 0;
+  const bool in_group = (g < G);
+  const bool leader = in_group && ((G > 1) ? (tid - g * Nmax == 0) : (tid == 0));
+  const int n_pass = (G > 1) ? 1 : (Nmax + kK3aThreads - 1) / kK3aThreads;
+  double mean[MPE_MAX_LEDS][3];
+  int num_valid = 0;
+  if (leader)
+    for (int j = 0; j < n_obj; ++j) mean[j][0] = mean[j][1] = mean[j][2] = 0;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int i = (G > 1) ? (tid - g * Nmax) : (pass * kK3aThreads + tid);
+    int found = 0;
+    if (in_group && fr[g].valid && i < fr[g].N) {
+      const CheckFrame& F = fr[g];
+      const int k = F.k, nu = k - 3;
+      int c0, c1, c2;
+      unrank_comb3_k3(k, i, c0, c1, c2);
+      const int l0 = F.corr[c0][0] - 1, l1 = F.corr[c1][0] - 1, l2 = F.corr[c2][0] - 1;
+      const int e0 = F.corr[c0][1] - 1, e1 = F.corr[c1][1] - 1, e2 = F.corr[c2][1] - 1;
+      P3PSetup S;
+      int rc = p3p_setup(v_make(F.bearing[e0][0], F.bearing[e0][1], F.bearing[e0][2]),
+                         v_make(F.bearing[e1][0], F.bearing[e1][1], F.bearing[e1][2]),
+                         v_make(F.bearing[e2][0], F.bearing[e2][1], F.bearing[e2][2]),
+                         v_make(mk[3 * l0], mk[3 * l0 + 1], mk[3 * l0 + 2]), v_make(mk[3 * l1], mk[3 * l1 + 1], mk[3 * l1 + 2]),
+                         v_make(mk[3 * l2], mk[3 * l2 + 1], mk[3 * l2 + 2]), S);
+      if (rc == 0) {
+        double min_sq = HUGE_VAL;
+        int best = 0;
+        for (int j = 0; j < 4; ++j) {
+          double H[12];
+          if (!p3p_solution(S, j, H)) continue;
+          if (!h_is_finite(H)) continue;                           // :479
+          double Hi[12], KT[12];
+          h_inverse(H, Hi);
+          kt_product(K, Hi, KT);
+          double bu[kMaxUnused], bv[kMaxUnused];
+          double dist[kMaxUnused * kMaxUnused];
+          int m = 0;
+          for (int l = 0; l < k; ++l) {                            // unused rows, in row order (:437-455)
+            if (l == c0 || l == c1 || l == c2) continue;
+            int led = F.corr[l][0] - 1;
+            kt_project(KT, mk[3 * led], mk[3 * led + 1], mk[3 * led + 2], bu[m], bv[m]);
+            ++m;
+          }
+          int ii = 0;
+          for (int l = 0; l < k; ++l) {
+            if (l == c0 || l == c1 || l == c2) continue;
+            int di = F.corr[l][1] - 1;
+            for (int jj = 0; jj < nu; ++jj) {
+              double dx = F.det[di][0] - bu[jj], dy = F.det[di][1] - bv[jj];
+              dist[ii * nu + jj] = sqrt(dx * dx + dy * dy);
+            }
+            ++ii;
+          }
+          double certainty;
+          double sq = squared_error_and_certainty(dist, nu, nu, a.pp.back_projection_pixel_tolerance, &certainty);
+          if (certainty >= a.pp.certainty_threshold) {             // :494
+            found = 1;
+            if (sq < min_sq) { min_sq = sq; best = j; }
+          }
+        }
+        if (found) {                                               // :506-518
+          double H[12], Hi[12];
+          p3p_solution(S, best, H);
+          h_inverse(H, Hi);
+          double* out = contrib + (size_t)tid * n_obj * 3;
+          for (int jj = 0; jj < n_obj; ++jj) {
+            double x = mk[3 * jj], y = mk[3 * jj + 1], z = mk[3 * jj + 2];
+            for (int r = 0; r < 3; ++r) {
+              double sacc = Hi[4 * r] * x;
+              sacc += Hi[4 * r + 1] * y;
+              sacc += Hi[4 * r + 2] * z;
+              sacc += Hi[4 * r + 3] * 1.0;
+              out[jj * 3 + r] = sacc;
+            }
+          }
+        }
+      }
+    }
+    found_s[tid] = found;
+    __syncthreads();
+    if (leader && fr[g].valid) {
+      // ordered accumulation over the subsets of this pass (subset order = reference loop order)
+      const int base = (G > 1) ? g * Nmax : 0;
+      const int cnt = (G > 1) ? fr[g].N : min(kK3aThreads, fr[g].N - pass * kK3aThreads);
+      for (int j = 0; j < cnt; ++j) {
+        if (!found_s[base + j]) continue;
+        ++num_valid;
+        const double* cj = contrib + (size_t)(base + j) * n_obj * 3;
+        for (int jj = 0; jj < n_obj; ++jj)
+          for (int r = 0; r < 3; ++r) mean[jj][r] = mean[jj][r] + cj[jj * 3 + r];
+      }
+    }
+    __syncthreads();
+  }
+  if (leader && fr[g].valid) {
+    const int f = f0 + g;
+    double* so = a.check_sums + (size_t)f * MPE_MAX_LEDS * 3;
+    for (int jj = 0; jj < n_obj; ++jj)
+      for (int r = 0; r < 3; ++r) so[jj * 3 + r] = mean[jj][r];
+    a.check_cnt[2 * f] = num_valid;
+    a.check_cnt[2 * f + 1] = fr[g].N;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b — refine_kernel: one THREAD per frame: acceptance test + Kabsch of checkCorrespondences, then the
+// Gauss-Newton of optimisePose, every sum in the reference's loop order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kK3bThreads = 64;
+
+__global__ void __launch_bounds__(kK3bThreads) refine_kernel(const K3Args a) {
+  const int f = blockIdx.x * kK3bThreads + threadIdx.x;
   if (f >= a.n_frames) return;
   if (a.active && !a.active[f]) return;
-  K3Warp& sh = shw[warp];
   const int n_obj = a.pp.n_obj;
   const double* K = a.cam.K;
-
+  const double* mk = a.pp.markers;
   const int n_det = a.n_det[f];
   int k = a.n_corr[f];
-  bool pose_path = (n_det >= 0 && n_det <= MPE_MAX_DET);   // memory-safety guard; n_det < 4 never reaches here with k >= 4 on the cold path
-  if (!pose_path) k = 0;
-  if (lane < n_det && pose_path) {
-    const double* det = a.det + (size_t)f * a.det_stride * 2;
-    double u = det[2 * lane], v = det[2 * lane + 1];
-    sh.det[lane][0] = u; sh.det[lane][1] = v;
-    double x = (u - K[2]) / K[0], y = (v - K[5]) / K[4], z = 1;       // calculateImageVectors :288-301
-    double n = sqrt(x * x + y * y + z * z);
-    sh.bearing[lane][0] = x / n; sh.bearing[lane][1] = y / n; sh.bearing[lane][2] = z / n;
-  }
-  if (lane < k) {
-    sh.corr[lane][0] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * lane];
-    sh.corr[lane][1] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * lane + 1];
-  }
-  __syncwarp();
+  if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;
+  if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
+  const double* det = a.det + (size_t)f * a.det_stride * 2;
+  const uint32_t* corr = a.corr + (size_t)f * 2 * MPE_MAX_LEDS;
 
   double T[12];   // predicted_pose_ top three rows, row-major
   for (int e = 0; e < 12; ++e) T[e] = a.pose_io[(size_t)f * 16 + e];
   int ok = 0;
 
-  // ------------------------------------------------------------------ checkCorrespondences
   if (a.mode == 0 || a.mode == 1) {
-    if (k >= 4) {                                                      // :401
-      const int N = k * (k - 1) * (k - 2) / 6;
-      const int nu = k - 3;                                            // total_unused_correspondences
-      double mean[MPE_MAX_LEDS][3];
-      for (int j = 0; j < n_obj; ++j) mean[j][0] = mean[j][1] = mean[j][2] = 0;
-      int num_valid = 0;
-      for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        int found = 0;
-        double contrib[MPE_MAX_LEDS][3];
-        if (i < N) {
-          int c0, c1, c2;
-          unrank_comb3_k3(k, i, c0, c1, c2);
-          const int l0 = sh.corr[c0][0] - 1, l1 = sh.corr[c1][0] - 1, l2 = sh.corr[c2][0] - 1;
-          const int e0 = sh.corr[c0][1] - 1, e1 = sh.corr[c1][1] - 1, e2 = sh.corr[c2][1] - 1;
-          const double* mk = a.pp.markers;
-          P3PSetup S;
-          int rc = p3p_setup(v_make(sh.bearing[e0][0], sh.bearing[e0][1], sh.bearing[e0][2]),
-                             v_make(sh.bearing[e1][0], sh.bearing[e1][1], sh.bearing[e1][2]),
-                             v_make(sh.bearing[e2][0], sh.bearing[e2][1], sh.bearing[e2][2]),
-                             v_make(mk[3 * l0], mk[3 * l0 + 1], mk[3 * l0 + 2]), v_make(mk[3 * l1], mk[3 * l1 + 1], mk[3 * l1 + 2]),
-                             v_make(mk[3 * l2], mk[3 * l2 + 1], mk[3 * l2 + 2]), S);
-          if (rc == 0) {
-            double min_sq = HUGE_VAL;
-            int best = 0;
-            for (int j = 0; j < 4; ++j) {
-              double H[12];
-              p3p_solution(S, j, H);
-              if (!h_is_finite(H)) continue;                           // :479
-              double Hi[12], KT[12];
-              h_inverse(H, Hi);
-              kt_product(K, Hi, KT);
-              double bu[kMaxUnused], bv[kMaxUnused];
-              double dist[kMaxUnused * kMaxUnused];
-              int m = 0;
-              for (int l = 0; l < k; ++l) {                            // unused rows, in row order (:437-455)
-                if (l == c0 || l == c1 || l == c2) continue;
-                int led = sh.corr[l][0] - 1;
-                kt_project(KT, mk[3 * led], mk[3 * led + 1], mk[3 * led + 2], bu[m], bv[m]);
-                ++m;
-              }
-              int ii = 0;
-              for (int l = 0; l < k; ++l) {
-                if (l == c0 || l == c1 || l == c2) continue;
-                int di = sh.corr[l][1] - 1;
-                for (int jj = 0; jj < nu; ++jj) {
-                  double dx = sh.det[di][0] - bu[jj], dy = sh.det[di][1] - bv[jj];
-                  dist[ii * nu + jj] = sqrt(dx * dx + dy * dy);
-                }
-                ++ii;
-              }
-              double certainty;
-              double sq = squared_error_and_certainty(dist, nu, nu, a.pp.back_projection_pixel_tolerance, &certainty);
-              if (certainty >= a.pp.certainty_threshold) {             // :494
-                found = 1;
-                if (sq < min_sq) { min_sq = sq; best = j; }
-              }
-            }
-            if (found) {                                               // :506-518
-              double H[12], Hi[12];
-              p3p_solution(S, best, H);
-              h_inverse(H, Hi);
-              for (int jj = 0; jj < n_obj; ++jj) {
-                double x = mk[3 * jj], y = mk[3 * jj + 1], z = mk[3 * jj + 2];
-                for (int r = 0; r < 3; ++r) {
-                  double sacc = Hi[4 * r] * x;
-                  sacc += Hi[4 * r + 1] * y;
-                  sacc += Hi[4 * r + 2] * z;
-                  sacc += Hi[4 * r + 3] * 1.0;
-                  contrib[jj][r] = sacc;
-                }
-              }
-            }
-          }
-        }
-        // ordered accumulation over the subsets of this pass
-        unsigned vmask = __ballot_sync(0xffffffffu, found != 0);
-        num_valid += __popc(vmask);
-        while (vmask) {
-          int src = __ffs(vmask) - 1;
-          vmask &= vmask - 1;
-          for (int jj = 0; jj < n_obj; ++jj)
-            for (int r = 0; r < 3; ++r) mean[jj][r] = mean[jj][r] + shfl_d(contrib[jj][r], src);
-        }
-      }
-      if ((double)num_valid / N >= a.pp.valid_correspondence_threshold) {   // :525
-        ok = 1;
-        // computeTransformation (:908-930)
-        const double* mk = a.pp.markers;
-        double mo[3] = {0, 0, 0}, mr[3] = {0, 0, 0};
-        for (int j = 0; j < n_obj; ++j)
-          for (int r = 0; r < 3; ++r) {
-            mean[j][r] = mean[j][r] / num_valid;
-            mo[r] = mo[r] + mk[3 * j + r];
-            mr[r] = mr[r] + mean[j][r];
-          }
-        for (int r = 0; r < 3; ++r) { mo[r] = mo[r] / (double)n_obj; mr[r] = mr[r] / (double)n_obj; }
-        double Hm[3][3], U[3][3], V[3][3];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) {
-            double sacc = 0;
-            for (int j = 0; j < n_obj; ++j) sacc += (mk[3 * j + r] - mo[r]) * (mean[j][c] - mr[c]);
-            Hm[r][c] = sacc;
-          }
-        svd3(Hm, U, V);
-        double Rm[3][3];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) Rm[r][c] = V[r][0] * U[c][0] + V[r][1] * U[c][1] + V[r][2] * U[c][2];   // V * U^T
+    const int num_valid = a.check_cnt[2 * f], N = a.check_cnt[2 * f + 1];
+    if (N > 0 && (double)num_valid / N >= a.pp.valid_correspondence_threshold) {   // :525
+      ok = 1;
+      const double* sums = a.check_sums + (size_t)f * MPE_MAX_LEDS * 3;
+      // computeTransformation (:908-930)
+      double mo[3] = {0, 0, 0}, mr[3] = {0, 0, 0};
+      for (int j = 0; j < n_obj; ++j)
         for (int r = 0; r < 3; ++r) {
-          double rt = Rm[r][0] * mo[0] + Rm[r][1] * mo[1] + Rm[r][2] * mo[2];
-          T[4 * r] = Rm[r][0]; T[4 * r + 1] = Rm[r][1]; T[4 * r + 2] = Rm[r][2];
-          T[4 * r + 3] = mr[r] - rt;
+          mo[r] = mo[r] + mk[3 * j + r];
+          mr[r] = mr[r] + sums[j * 3 + r] / num_valid;
         }
+      for (int r = 0; r < 3; ++r) { mo[r] = mo[r] / (double)n_obj; mr[r] = mr[r] / (double)n_obj; }
+      double Hm[3][3], U[3][3], V[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double sacc = 0;
+          for (int j = 0; j < n_obj; ++j) sacc += (mk[3 * j + r] - mo[r]) * (sums[j * 3 + c] / num_valid - mr[c]);
+          Hm[r][c] = sacc;
+        }
+      svd3(Hm, U, V);
+      double Rm[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Rm[r][c] = V[r][0] * U[c][0] + V[r][1] * U[c][1] + V[r][2] * U[c][2];   // V * U^T
+      for (int r = 0; r < 3; ++r) {
+        double rt = Rm[r][0] * mo[0] + Rm[r][1] * mo[1] + Rm[r][2] * mo[2];
+        T[4 * r] = Rm[r][0]; T[4 * r + 1] = Rm[r][1]; T[4 * r + 2] = Rm[r][2];
+        T[4 * r + 3] = mr[r] - rt;
       }
     }
   } else {
     ok = 1;   // mode 2: caller supplies correspondences and the starting pose
   }
 
-  // ------------------------------------------------------------------ optimisePose
   int iters = 0;
-  double cov[36];
   bool ran_gn = false;
+  double A[36];
   if (ok && (a.mode == 0 || a.mode == 2)) {
     ran_gn = true;
     const double fx = K[0], fy = K[4];
-    const double* mk = a.pp.markers;
-    const bool lane_active = (lane < k) && (sh.corr[lane < k ? lane : 0][1] != 0);   // :761
-    double ox = 0, oy = 0, oz = 0, ix = 0, iy = 0;
-    if (lane_active) {
-      int led = sh.corr[lane][0] - 1, di = sh.corr[lane][1] - 1;
-      ox = mk[3 * led]; oy = mk[3 * led + 1]; oz = mk[3 * led + 2];
-      ix = sh.det[di][0]; iy = sh.det[di][1];
-    }
-    const unsigned amask = __ballot_sync(0xffffffffu, lane_active);
-    double A[36], b[6], dT[6];
+    double b[6], dT[6];
     for (int e = 0; e < 36; ++e) A[e] = 0;
     for (int it = 0; it < 500; ++it) {                                  // max_itr :738
-      double jt[27];   // 21 unique J^T J entries (upper triangle, row-major) + 6 J^T e entries
-      if (lane_active) {
-        double KT[12], pu, pv;
-        kt_product(K, T, KT);                                           // project2d :251-268
+      for (int e = 0; e < 36; ++e) A[e] = 0;
+      for (int e = 0; e < 6; ++e) b[e] = 0;
+      double KT[12];
+      kt_product(K, T, KT);                                             // project2d :251-268 (same KT for every point)
+      for (int j = 0; j < k; ++j) {                                     // :759
+        const uint32_t led1 = corr[2 * j], det1 = corr[2 * j + 1];
+        if (det1 == 0) continue;                                        // :761
+        const int led = (int)led1 - 1, di = (int)det1 - 1;
+        const double ox = mk[3 * led], oy = mk[3 * led + 1], oz = mk[3 * led + 2];
+        double pu, pv;
         kt_project(KT, ox, oy, oz, pu, pv);
-        double e0 = ix - pu, e1 = iy - pv;                              // :769
+        const double e0 = det[2 * di] - pu, e1 = det[2 * di + 1] - pv;  // :769
         // computeJacobian :932-960
         double x = T[0] * ox + T[1] * oy + T[2] * oz + T[3] * 1.0;
         double y = T[4] * ox + T[5] * oy + T[6] * oz + T[7] * 1.0;
@@ -455,60 +513,57 @@ __global__ void __launch_bounds__(32 * kK3WarpsPerCta) validate_refine_kernel(co
         double J0[6], J1[6];
         J0[0] = 1 / z * fx; J0[1] = 0; J0[2] = -x / z_2 * fx; J0[3] = -x * y / z_2 * fx; J0[4] = (1 + (x * x / z_2)) * fx; J0[5] = -y / z * fx;
         J1[0] = 0; J1[1] = 1 / z * fy; J1[2] = -y / z_2 * fy; J1[3] = -(1 + y * y / z_2) * fy; J1[4] = x * y / z_2 * fy; J1[5] = x / z * fy;
-        int q = 0;
-        for (int r = 0; r < 6; ++r)
-          for (int c = r; c < 6; ++c) jt[q++] = J0[r] * J0[c] + J1[r] * J1[c];
-        for (int r = 0; r < 6; ++r) jt[21 + r] = J0[r] * e0 + J1[r] * e1;
-      } else {
-        for (int q = 0; q < 27; ++q) jt[q] = 0;
-      }
-      double acc[27];
-      for (int q = 0; q < 27; ++q) acc[q] = 0;
-      unsigned mm = amask;
-      while (mm) {                                                      // correspondence order (:759)
-        int src = __ffs(mm) - 1;
-        mm &= mm - 1;
-        for (int q = 0; q < 27; ++q) acc[q] += shfl_d(jt[q], src);
-      }
-      {
-        int q = 0;
-        for (int r = 0; r < 6; ++r)
-          for (int c = r; c < 6; ++c) { A[r * 6 + c] = acc[q]; A[c * 6 + r] = acc[q]; ++q; }
-        for (int r = 0; r < 6; ++r) b[r] = acc[21 + r];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) A[r * 6 + c] += J0[r] * J0[c] + J1[r] * J1[c];
+          b[r] += J0[r] * e0 + J1[r] * e1;
+        }
       }
       ldlt_solve6(A, b, dT);                                            // :778
       exp_map_left_multiply(dT, T);                                     // :781
       ++iters;
       double mx = -1;                                                   // norm_max :1073-1085
+#pragma unroll
       for (int q = 0; q < 6; ++q) { double av = fabs(dT[q]); if (av > mx) mx = av; }
-#ifdef MPE_DEBUG_GN
-      if (lane == 0 && f == 0 && iters == 1) {
-        for (int r = 0; r < 6; ++r) printf("A[%d] %.9e %.9e %.9e %.9e %.9e %.9e | b %.9e\n", r, A[r*6], A[r*6+1], A[r*6+2], A[r*6+3], A[r*6+4], A[r*6+5], b[r]);
-        printf("amask %x k %d\n", amask, k);
-      }
-      if (lane == 0 && f == 0) printf("GN it %d mx %.3e dT %.3e %.3e %.3e %.3e %.3e %.3e | A00 %.6e A55 %.6e b0 %.3e T3 %.9f %.9f %.9f\n", iters, mx, dT[0], dT[1], dT[2], dT[3], dT[4], dT[5], A[0], A[35], b[0], T[3], T[7], T[11]);
-#endif
       if (mx <= 1e-13) break;                                           // :786
     }
-    inverse6(A, cov);                                                   // :790
   }
 
-  if (lane == 0) {
-    double* po = a.pose_io + (size_t)f * 16;
-    if (ok) {
-      for (int e = 0; e < 12; ++e) po[e] = T[e];
-      po[12] = 0; po[13] = 0; po[14] = 0; po[15] = 1;
-    }
-    if (ran_gn && a.cov) for (int e = 0; e < 36; ++e) a.cov[(size_t)f * 36 + e] = cov[e];
-    if (a.ok) a.ok[f] = ok;
-    if (a.iters) a.iters[f] = iters;
-    if (a.updated) a.updated[f] = (ok && ran_gn) ? 1 : 0;
+  double* po = a.pose_io + (size_t)f * 16;
+  if (ok) {
+    for (int e = 0; e < 12; ++e) po[e] = T[e];
+    po[12] = 0; po[13] = 0; po[14] = 0; po[15] = 1;
   }
+  if (ran_gn && a.cov) {
+    double cov[36];
+    inverse6(A, cov);                                                   // :790
+    for (int e = 0; e < 36; ++e) a.cov[(size_t)f * 36 + e] = cov[e];
+  }
+  if (a.ok) a.ok[f] = ok;
+  if (a.iters) a.iters[f] = iters;
+  if (a.updated) a.updated[f] = (ok && ran_gn) ? 1 : 0;
 }
 
 cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
-  int grid = (a.n_frames + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
-  validate_refine_kernel<<<grid, 32 * kK3WarpsPerCta, 0, st>>>(a);
+  if (a.mode == 0 || a.mode == 1) {
+    const int n_obj = a.pp.n_obj;
+    int Nmax = (n_obj >= 4) ? n_obj * (n_obj - 1) * (n_obj - 2) / 6 : 1;
+    int G = (Nmax <= kK3aThreads) ? kK3aThreads / Nmax : 1;
+    if (G > 32) G = 32;
+    size_t smem = (size_t)G * sizeof(CheckFrame) + (size_t)kK3aThreads * n_obj * 3 * sizeof(double) + kK3aThreads * sizeof(int);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    int grid = (a.n_frames + G - 1) / G;
+    check_kernel<<<grid, kK3aThreads, smem, st>>>(a, G, Nmax);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -36,7 +37,8 @@ struct DevBuffers {
   int* updated = nullptr;          // [max_batch]
   Roi* rois = nullptr;             // [max_batch]
   mpe_result* results = nullptr;   // [max_batch]
-  double* scratch_d = nullptr;     // p3p stage call
+  double* check_sums = nullptr;    // [max_batch][MPE_MAX_LEDS*3]
+  int* check_cnt = nullptr;        // [max_batch][2]
 };
 
 }  // namespace
@@ -109,6 +111,17 @@ bool gaussian_taps_8u(double sigma, int* radius, uint32_t taps[kMaxTaps]) {
   taps[n2] = (uint32_t)(256 - tot);
   *radius = n2;
   return true;
+}
+
+// Largest double x such that sqrt(x) < tol in IEEE arithmetic (sqrt is correctly rounded and monotonic), so that the sweep can
+// test the squared distance: "sqrt(d2) < tol" (pose_estimator.cpp:671,689)  <=>  "d2 <= x".  -1 when no d2 >= 0 qualifies.
+double sqrt_less_than_bound(double tol) {
+  if (!(tol > 0)) return -1.0;
+  if (std::isinf(tol)) return std::numeric_limits<double>::max();
+  double x = tol * tol;
+  while (std::sqrt(x) >= tol) x = std::nextafter(x, 0.0);
+  while (std::sqrt(std::nextafter(x, INFINITY)) < tol) x = std::nextafter(x, INFINITY);
+  return x;
 }
 
 // Combinations::numCombinations with the reference's unsigned factorial (combinations.cpp:34-45)
@@ -270,10 +283,12 @@ int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const ui
   k.iters = c->d.iters + slot0;
   k.updated = c->d.updated + slot0;
   k.active = active;
+  k.check_sums = c->d.check_sums + (size_t)slot0 * MPE_MAX_LEDS * 3;
+  k.check_cnt = c->d.check_cnt + (size_t)slot0 * 2;
   time_begin(c, 3, st);
   CUDA_TRY(c, launch_validate_refine(k, st));
   time_end(c, 3, st);
-  ++c->launches;
+  c->launches += (mode == 2) ? 1 : 2;
   return MPE_OK;
 }
 
@@ -385,6 +400,8 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.updated, B));
   CREATE_TRY(dev_alloc(&c->d.rois, B));
   CREATE_TRY(dev_alloc(&c->d.results, B));
+  CREATE_TRY(dev_alloc(&c->d.check_sums, B * MPE_MAX_LEDS * 3));
+  CREATE_TRY(dev_alloc(&c->d.check_cnt, B * 2));
   CREATE_TRY(cudaMemset(c->d.n_corr, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.flags, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.corr, 0, B * 2 * MPE_MAX_LEDS * sizeof(uint32_t)));
@@ -393,6 +410,7 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   for (int i = 0; i < 8; ++i) CREATE_TRY(cudaEventCreate(&c->ev[i]));
   // PoseEstimator::PoseEstimator() defaults (pose_estimator.cpp:36-39)
   c->pp.back_projection_pixel_tolerance = 3;
+  c->pp.back_proj_sq_max = sqrt_less_than_bound(3.0);
   c->pp.nearest_neighbour_pixel_tolerance = 5;
   c->pp.certainty_threshold = 0.75;
   c->pp.valid_correspondence_threshold = 0.7;
@@ -412,7 +430,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
   cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.done); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
-  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.scratch_d);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt);
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
@@ -457,6 +475,7 @@ int mpe_set_params(mpe_ctx* c, const mpe_params* p) {
     return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "] (sigma in about (0.09, 1.41))");
   c->params = *p;
   c->pp.back_projection_pixel_tolerance = p->back_projection_pixel_tolerance;
+  c->pp.back_proj_sq_max = sqrt_less_than_bound(p->back_projection_pixel_tolerance);
   c->pp.nearest_neighbour_pixel_tolerance = p->nearest_neighbour_pixel_tolerance;
   c->pp.certainty_threshold = p->certainty_threshold;
   c->pp.valid_correspondence_threshold = p->valid_correspondence_threshold;

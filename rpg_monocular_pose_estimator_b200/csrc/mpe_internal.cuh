@@ -30,6 +30,7 @@ struct DevPoseParams {
   double nearest_neighbour_pixel_tolerance;
   double certainty_threshold;
   double valid_correspondence_threshold;
+  double back_proj_sq_max;     // largest x with sqrt(x) < back_projection_pixel_tolerance (exact stand-in for the sqrt)
   uint32_t histogram_threshold;
   int n_obj;
   double markers[3 * MPE_MAX_LEDS];
@@ -106,6 +107,8 @@ struct K3Args {
   int* iters;                // [n_frames]
   int* updated;              // [n_frames]
   const uint8_t* active;     // optional
+  double* check_sums;        // [n_frames][MPE_MAX_LEDS*3]  sum of H^-1 X_j over the valid subsets (K3a -> K3b)
+  int* check_cnt;            // [n_frames][2]  number of valid subsets, number of subsets
 };
 
 // ---- launchers (defined next to the kernels) ----

@@ -34,10 +34,26 @@ __device__ __forceinline__ cplx c_polar(double rho, double theta) {
   return c_make(rho * c, rho * s);
 }
 
-// std::pow(const complex<double>&, const double&)
-__device__ __forceinline__ cplx c_pow_real(cplx z, double y) {
-  if (z.im == 0.0 && z.re > 0.0) return c_make(pow(z.re, y), 0.0);
-  // std::log(z) = (log|z|, arg z)
+// std::pow(const complex<double>&, const double&) as libstdc++ defines it, specialised for the three exponents
+// solveQuartic uses (2.0, 3.0, 1.0/3.0):
+//   positive-real base -> real pow: x*x, x*x*x (what a correctly rounded pow returns for x^2; within 1 ulp for x^3) and cbrt;
+//   otherwise          -> polar(exp(y * log|z|), y * arg z).  For a negative-real base arg z = +-pi, so the angle y*pi is a
+//                         constant: its sine/cosine are the values glibc's sincos returns for fl(y*pi) (hex literals below),
+//                         and log|z| needs no hypot.
+template <int kExp>   // 2, 3, or 0 for 1/3
+__device__ __forceinline__ cplx c_pow_real(cplx z) {
+  const double y = (kExp == 2) ? 2.0 : (kExp == 3) ? 3.0 : (1.0 / 3.0);
+  if (z.im == 0.0 && z.re > 0.0) {
+    double r = (kExp == 2) ? z.re * z.re : (kExp == 3) ? z.re * z.re * z.re : cbrt(z.re);
+    return c_make(r, 0.0);
+  }
+  if (z.im == 0.0 && z.re < 0.0) {
+    // sin/cos of fl(y * pi) from glibc 2.39 (= what the reference's libm returns); sign of the angle follows arg z = copysign(pi, im)
+    const double sn = (kExp == 2) ? -0x1.1a62633145c07p-52 : (kExp == 3) ? 0x1.a79394c9e8a0ap-52 : 0x1.bb67ae8584caap-1;
+    const double cs = (kExp == 2) ? 1.0 : (kExp == 3) ? -1.0 : 0x1.0000000000001p-1;
+    double rho = exp(y * log(-z.re));
+    return c_make(rho * cs, rho * (signbit(z.im) ? -sn : sn));
+  }
   double lr, li;
   if (z.re == 0.0 && z.im == 0.0) {          // glibc clog(0): (-inf, signbit(re) ? pi : 0)
     lr = -1.0 / fabs(z.re);
@@ -132,12 +148,12 @@ __device__ __forceinline__ void solve_quartic(const double factors[5], double re
   cplx P = c_make(-alpha_pw2 / 12 - gamma, 0.0);
   cplx Q = c_make(-alpha_pw3 / 108 + alpha * gamma / 3 - (beta * beta) / 8, 0.0);
   // R = -Q/2 + sqrt(pow(Q,2)/4 + pow(P,3)/27)
-  cplx R = c_add(c_divr(c_neg(Q), 2.0), c_sqrt(c_add(c_divr(c_pow_real(Q, 2.0), 4.0), c_divr(c_pow_real(P, 3.0), 27.0))));
-  cplx U = c_pow_real(R, 1.0 / 3.0);
+  cplx R = c_add(c_divr(c_neg(Q), 2.0), c_sqrt(c_add(c_divr(c_pow_real<2>(Q), 4.0), c_divr(c_pow_real<3>(P), 27.0))));
+  cplx U = c_pow_real<0>(R);
   cplx y;
   double m56a = -5.0 * alpha / 6.0;
   if (U.re == 0.0)
-    y = r_sub(m56a, c_pow_real(Q, 1.0 / 3.0));
+    y = r_sub(m56a, c_pow_real<0>(Q));
   else
     y = c_add(r_sub(m56a, c_div(P, c_scale(3.0, U))), U);
 
@@ -235,7 +251,9 @@ __device__ __forceinline__ int p3p_setup(v3 f1, v3 f2, v3 f3in, v3 P1, v3 P2, v3
 }
 
 // Back-substitution of root i (p3p.cpp:193-233).  H = [R | C] row-major 3x4 (camera -> world).
-__device__ __forceinline__ void p3p_solution(const P3PSetup& S, int i, double H[12]) {
+// Returns false (H untouched) when a NaN in the root-dependent scalars makes every entry of R NaN, i.e. exactly in
+// cases that PoseEstimator::isFinite would reject afterwards; saves the two 3x3 products for dead hypotheses.
+__device__ __forceinline__ bool p3p_solution(const P3PSetup& S, int i, double H[12]) {
   double root = S.roots[i];
   double cot_alpha = (-S.f_1 * S.p_1 / S.f_2 - root * S.p_2 + S.d_12 * S.b) / (-S.f_1 * root * S.p_2 / S.f_2 + S.p_1 - S.d_12);
   double cos_theta = root;
@@ -243,6 +261,7 @@ __device__ __forceinline__ void p3p_solution(const P3PSetup& S, int i, double H[
   double sin_alpha = sqrt(1 / (cot_alpha * cot_alpha + 1));
   double cos_alpha = sqrt(1 - sin_alpha * sin_alpha);
   if (cot_alpha < 0) cos_alpha = -cos_alpha;
+  if (isnan(sin_theta) || isnan(sin_alpha)) return false;   // R(0,2) = -sin_alpha*sin_theta etc. would all be NaN
 
   double k = (sin_alpha * S.b + cos_alpha);
   double C0 = S.d_12 * cos_alpha * k;
@@ -270,6 +289,7 @@ __device__ __forceinline__ void p3p_solution(const P3PSetup& S, int i, double H[
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) H[4 * r + c] = M[r][0] * T[0][c] + M[r][1] * T[1][c] + M[r][2] * T[2][c];
+  return true;
 }
 
 // PoseEstimator::isFinite on [H; 0 0 0 1] (pose_estimator.cpp:856-860): false for NaN and +-Inf.
