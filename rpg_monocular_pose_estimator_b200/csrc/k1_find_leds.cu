@@ -114,17 +114,19 @@ __device__ __forceinline__ TileCoord decode_tile(const K1Geom& g, int t) {
 // K1a
 // ------------------------------------------------------------------------------------------------
 // Shared-memory layout (dynamic):
-//   [0, 64)                              mbarriers (one per stage)
-//   hot   [rows][hot_wpr]   u32          exact "word holds a byte > thr" bits of the current tile
-//   omask [kTileRows][om_wpr] u32        non-zero bits of the blurred output rows of the current tile
-//   misc  [4] u32                        list length, row-flag accumulator
-//   list  [kTileRows * box_w] u16        compacted (row, word) pairs that need the exact blur
-//   stage ring: kStages x rows x box_w u32 (1024-byte aligned start)
+//   [0, 64)                               mbarriers (one per stage)
+//   misc  [4] u32                         [0] #hot units, [1] #active words, [2] row mask of the tile's output
+//   act   [kTileRows][hot_wpr] u32        output words whose source neighbourhood holds a byte > thr   (kept all-zero between tiles)
+//   omask [kTileRows][om_wpr] u32         non-zero bits of the blurred output rows                     (kept all-zero between tiles)
+//   hotu  [rows * box_w / 4] u16          16-byte units that may hold a byte > thr (conservative: OR of the 4 words)
+//   list  [kTileRows * box_w] u16         compacted (row << 8 | word) pairs that need the exact blur
+//   stage ring: kStages x stage_stride bytes (1024-byte aligned start)
 struct K1Smem {
   uint64_t* bars;
-  uint32_t* hot;
-  uint32_t* omask;
   uint32_t* misc;
+  uint32_t* act;
+  uint32_t* omask;
+  uint16_t* hotu;
   uint16_t* list;
   uint8_t* ring;
 };
@@ -132,7 +134,10 @@ struct K1Smem {
 __host__ __device__ inline size_t k1_ring_offset(int rows, int box_w, int tw_px) {
   int hot_wpr = (box_w + 31) >> 5;
   int om_wpr = (tw_px + 31) >> 5;
-  size_t off = 64 + (size_t)(rows * hot_wpr + kTileRows * om_wpr + 4) * 4 + (size_t)kTileRows * box_w * 2;
+  size_t off = 64 + (size_t)(4 + kTileRows * hot_wpr + kTileRows * om_wpr) * 4;
+  off += (size_t)(rows * (box_w >> 2)) * 2;       // hotu
+  off = (off + 3) & ~(size_t)3;
+  off += (size_t)kTileRows * box_w * 2;           // list
   return (off + 1023) & ~(size_t)1023;
 }
 
@@ -147,18 +152,27 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
   const int om_wpr = (g.tw_px + 31) >> 5;
   const uint32_t stage_bytes = (uint32_t)(kRows * row_bytes);          // bytes one TMA box delivers
   const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;           // TMA destinations must be 128-byte aligned
+  const int units_per_row = box_w >> 2;
+  const int n_units = kRows * units_per_row;
 
   K1Smem sm;
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
-  sm.hot = reinterpret_cast<uint32_t*>(smem_raw + 64);
-  sm.omask = sm.hot + kRows * hot_wpr;
-  sm.misc = sm.omask + kTileRows * om_wpr;
-  sm.list = reinterpret_cast<uint16_t*>(sm.misc + 4);
+  sm.misc = reinterpret_cast<uint32_t*>(smem_raw + 64);
+  sm.act = sm.misc + 4;
+  sm.omask = sm.act + kTileRows * hot_wpr;
+  sm.hotu = reinterpret_cast<uint16_t*>(sm.omask + kTileRows * om_wpr);
+  {
+    size_t off = (size_t)(reinterpret_cast<uint8_t*>(sm.hotu) - smem_raw) + (size_t)n_units * 2;
+    off = (off + 3) & ~(size_t)3;
+    sm.list = reinterpret_cast<uint16_t*>(smem_raw + off);
+  }
   sm.ring = smem_raw + k1_ring_offset(kRows, box_w, g.tw_px);
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int n_tiles = g.n_frames * g.n_strips * g.n_ct;
 
+  for (int i = tid; i < 4 + kTileRows * hot_wpr + kTileRows * om_wpr; i += kK1Threads) sm.misc[i] = 0u;   // misc, act, omask contiguous
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&sm.bars[s], 1);
     fence_barrier_init();
@@ -185,9 +199,6 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
     for (int s = 0; s < kStages; ++s) produce_one();
 
   const uint32_t thr_k = (uint32_t)a.thr_k;
-  const int units_per_row = box_w >> 2;
-  const int n_units = kRows * units_per_row;
-  const int warp = tid >> 5, lane = tid & 31;
 
   int ccount = 0;   // valid tiles consumed by this CTA
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -198,68 +209,74 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
     ++ccount;
     mbar_wait(&sm.bars[stage], parity);
     const uint8_t* tile_smem = sm.ring + (size_t)stage * stage_stride;
-
-    // ---------------- dense phase: is anything above the threshold in this tile? ----------------
-    uint32_t local_hot = 0;
     const uint4* units = reinterpret_cast<const uint4*>(tile_smem);
-    for (int u = tid; u < n_units; u += kK1Threads) {
-      uint4 v = units[u];
-      uint32_t o = (v.x | v.y) | (v.z | v.w);
-      local_hot |= any_byte_gt<kLowThr>(o, thr_k);
-    }
-    int any_hot = __syncthreads_or((int)local_hot);
 
-    const int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
-    const int y0 = c.roi.y + c.s * kTileRows - R;
-    const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
+    // ---------------- dense phase: which 16-byte units may hold a byte above the threshold? ----------------
+    // four units (64 bytes) per test: OR all sixteen words, one SWAR compare; split up only when that is positive
+    for (int base = 0; base < n_units; base += 4 * kK1Threads) {
+      const int u0 = base + tid;
+      uint4 v0 = (u0 < n_units) ? units[u0] : make_uint4(0, 0, 0, 0);
+      uint4 v1 = (u0 + kK1Threads < n_units) ? units[u0 + kK1Threads] : make_uint4(0, 0, 0, 0);
+      uint4 v2 = (u0 + 2 * kK1Threads < n_units) ? units[u0 + 2 * kK1Threads] : make_uint4(0, 0, 0, 0);
+      uint4 v3 = (u0 + 3 * kK1Threads < n_units) ? units[u0 + 3 * kK1Threads] : make_uint4(0, 0, 0, 0);
+      uint32_t o0 = (v0.x | v0.y) | (v0.z | v0.w), o1 = (v1.x | v1.y) | (v1.z | v1.w);
+      uint32_t o2 = (v2.x | v2.y) | (v2.z | v2.w), o3 = (v3.x | v3.y) | (v3.z | v3.w);
+      if (any_byte_gt<kLowThr>((o0 | o1) | (o2 | o3), thr_k)) {
+        if (any_byte_gt<kLowThr>(o0, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)u0;
+        if (any_byte_gt<kLowThr>(o1, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + kK1Threads);
+        if (any_byte_gt<kLowThr>(o2, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + 2 * kK1Threads);
+        if (any_byte_gt<kLowThr>(o3, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + 3 * kK1Threads);
+      }
+    }
+    __syncthreads();
+    const int n_hot = (int)sm.misc[0];
     uint32_t* flag_ptr = a.rowflags + (size_t)c.f * g.flags_per_frame + c.s * g.n_ct + c.ct;
 
-    if (!any_hot) {
+    if (n_hot == 0) {
       if (tid == 0) *flag_ptr = 0u;
     } else {
       // ---------------- sparse phase ----------------
-      for (int i = tid; i < kRows * hot_wpr + kTileRows * om_wpr + 4; i += kK1Threads) sm.hot[i] = 0u;   // hot, omask, misc are contiguous
-      __syncthreads();
-      // exact per-word hot bits
-      for (int u = tid; u < n_units; u += kK1Threads) {
-        uint4 v = units[u];
-        uint32_t o = (v.x | v.y) | (v.z | v.w);
-        if (any_byte_gt<kLowThr>(o, thr_k)) {
-          int row = u / units_per_row;
-          int w0 = (u - row * units_per_row) * 4;
-          uint32_t bits = (any_byte_gt<kLowThr>(v.x, thr_k) ? 1u : 0u) | (any_byte_gt<kLowThr>(v.y, thr_k) ? 2u : 0u) |
-                          (any_byte_gt<kLowThr>(v.z, thr_k) ? 4u : 0u) | (any_byte_gt<kLowThr>(v.w, thr_k) ? 8u : 0u);
-          if (bits) atomicOr(&sm.hot[row * hot_wpr + (w0 >> 5)], bits << (w0 & 31));
-        }
-      }
-      __syncthreads();
-      // words whose (2R+1) x 3-word source neighbourhood holds a hot word: vertical OR, horizontal dilation
-      for (int item = tid; item < out_rows * hot_wpr; item += kK1Threads) {
-        int r = item / hot_wpr, hw = item - r * hot_wpr;
-        uint32_t v = 0, vl = 0, vr = 0;
+      const int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
+      const int y0 = c.roi.y + c.s * kTileRows - R;
+      const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
+      // (B) exact per-word test of the hot units; every hot source word marks the output words it can influence:
+      //     output rows row-2R .. row, words j-1 .. j+1
+      for (int t = tid; t < n_hot; t += kK1Threads) {
+        const int u = sm.hotu[t];
+        const uint4 v = units[u];
+        const int row = u / units_per_row;
+        const int w0 = (u - row * units_per_row) * 4;
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int dr = 0; dr <= 2 * R; ++dr) {
-          const uint32_t* hrow = sm.hot + (r + dr) * hot_wpr;
-          v |= hrow[hw];
-          if (hw > 0) vl |= hrow[hw - 1];
-          if (hw + 1 < hot_wpr) vr |= hrow[hw + 1];
-        }
-        uint32_t d = v | (v << 1) | (v >> 1) | (vl >> 31) | (vr << 31);
-        while (d) {
-          int bit = __ffs(d) - 1;
-          d &= d - 1;
-          int j = hw * 32 + bit;
-          if (j < box_w) {
-            uint32_t slot = atomicAdd(&sm.misc[0], 1u);
-            sm.list[slot] = (uint16_t)((r << 8) | j);
+        for (int q = 0; q < 4; ++q) {
+          if (!any_byte_gt<kLowThr>(wv[q], thr_k)) continue;
+          const int j = w0 + q;
+          const int r_lo = max(row - 2 * R, 0), r_hi = min(row, out_rows - 1);
+          for (int jj = max(j - 1, 0); jj <= min(j + 1, box_w - 1); ++jj) {
+            const uint32_t bit = 1u << (jj & 31);
+            for (int r = r_lo; r <= r_hi; ++r) atomicOr(&sm.act[r * hot_wpr + (jj >> 5)], bit);
           }
         }
       }
       __syncthreads();
-      const int n_list = (int)sm.misc[0];
+      // (C) compact the marked words into a list; the bitmap is cleared on the way (stays clean for the next tile)
+      for (int item = tid; item < out_rows * hot_wpr; item += kK1Threads) {
+        uint32_t d = sm.act[item];
+        if (!d) continue;
+        sm.act[item] = 0u;
+        const int r = item / hot_wpr, hw = item - r * hot_wpr;
+        while (d) {
+          const int bit = __ffs(d) - 1;
+          d &= d - 1;
+          sm.list[atomicAdd(&sm.misc[1], 1u)] = (uint16_t)((r << 8) | (hw * 32 + bit));
+        }
+      }
+      __syncthreads();
+      const int n_list = (int)sm.misc[1];
       const int tile_x0 = c.roi.x + c.ct * g.tw_px;                      // output pixel range of this tile
       const int tile_x1 = min(c.roi.x + c.roi.w, tile_x0 + g.tw_px);
       const uint32_t thr = (uint32_t)a.threshold;
+      // (D) exact fixed-point blur of the listed words (4 output pixels each)
       for (int e = tid; e < n_list; e += kK1Threads) {
         const int r = sm.list[e] >> 8, j = sm.list[e] & 0xff;
         const int first_px = 4 * x_elem0 + 4 * j;                        // image x of the word's first pixel
@@ -267,8 +284,7 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
         const int Y = y0 + R + r;                                        // image row of this output row
         const bool interior = (first_px - R >= c.roi.x) && (first_px + 3 + R < c.roi.x + c.roi.w) &&
                               (Y - R >= c.roi.y) && (Y + R < c.roi.y + c.roi.h);
-        // horizontal pass for the 2R+1 source rows, 4 output pixels each (8.8 fixed point)
-        uint32_t hsum[2 * R + 1][4];
+        uint32_t hsum[2 * R + 1][4];                                     // horizontal pass, 8.8 fixed point
 #pragma unroll
         for (int dr = 0; dr <= 2 * R; ++dr) {
           uint32_t px[4 + 2 * R];
@@ -295,33 +311,47 @@ __global__ void __launch_bounds__(kK1Threads) find_leds_kernel(const __grid_cons
             hsum[dr][q] = acc;
           }
         }
+        uint32_t bits = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           int X = first_px + q;
-          if (X < tile_x0 || X >= tile_x1) continue;
           uint32_t acc = 0;
 #pragma unroll
           for (int dr = 0; dr <= 2 * R; ++dr) acc += a.taps[dr] * hsum[dr][q];
-          if ((acc + 32768u) >> 16) {                                     // 16.16 -> u8 round-half-up, non-zero?
-            int bx = X - tile_x0;
-            atomicOr(&sm.omask[r * om_wpr + (bx >> 5)], 1u << (bx & 31));
-          }
+          if (X >= tile_x0 && X < tile_x1 && ((acc + 32768u) >> 16)) bits |= 1u << q;     // 16.16 -> u8 round-half-up, non-zero?
+        }
+        if (bits) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (bits & (1u << q)) {
+              int bx = first_px + q - tile_x0;
+              atomicOr(&sm.omask[r * om_wpr + (bx >> 5)], 1u << (bx & 31));
+            }
+          atomicOr(&sm.misc[2], 1u << r);
         }
       }
       __syncthreads();
-      // write-out: one warp per row; rows without foreground are not written (their flag bit stays 0)
+      // (E) write-out of the rows that contain foreground; rows without foreground are not written (flag bit 0)
+      const uint32_t rowmask = sm.misc[2];
+      __syncthreads();
+      if (tid == 0) {
+        *flag_ptr = rowmask;
+        sm.misc[0] = 0u; sm.misc[1] = 0u; sm.misc[2] = 0u;
+      }
       const int words_per_ct = g.tw_px >> 5;   // only used when n_ct > 1 (tw_px is a multiple of 32 then)
-      for (int r = warp; r < out_rows; r += kK1Threads / 32) {
-        uint32_t nz = 0;
-        for (int w = lane; w < om_wpr; w += 32) nz |= sm.omask[r * om_wpr + w];
-        if (__ballot_sync(0xffffffffu, nz != 0)) {
-          uint32_t* dst = a.mask + ((size_t)c.f * g.mask_rows + (c.s * kTileRows + r)) * g.mask_wpr + c.ct * words_per_ct;
-          for (int w = lane; w < om_wpr; w += 32) dst[w] = sm.omask[r * om_wpr + w];
-          if (lane == 0) atomicOr(&sm.misc[1], 1u << r);
+      uint32_t rm = rowmask;
+      int nth = 0;
+      while (rm) {
+        const int r = __ffs(rm) - 1;
+        rm &= rm - 1;
+        if ((nth++ & (kK1Threads / 32 - 1)) != warp) continue;
+        uint32_t* dst = a.mask + ((size_t)c.f * g.mask_rows + (c.s * kTileRows + r)) * g.mask_wpr + c.ct * words_per_ct;
+        for (int w = lane; w < om_wpr; w += 32) {
+          dst[w] = sm.omask[r * om_wpr + w];
+          sm.omask[r * om_wpr + w] = 0u;
         }
       }
       __syncthreads();
-      if (tid == 0) *flag_ptr = sm.misc[1];
     }
     // every thread is past a barrier that follows its last read of this stage: refill it
     if (tid == 0) produce_one();
@@ -499,10 +529,23 @@ __device__ bool is_enclosed(const MaskView& m, int px, int py) {
       blocked_l = v != 0;
     }
     if (!blocked_l) return false;
-    // the component itself extends to the right of its start pixel; skip its own run first
-    int x = px;
-    while (x < m.w && mv_bit(m, x, py)) ++x;
-    for (; x < m.w && !blocked_r; ++x) blocked_r = mv_bit(m, x, py);
+    // right ray, word-wise: skip the component's own run that starts at px, then look for any further foreground
+    bool in_run = true;
+    for (int wi = wi0; wi < m.wpr && !blocked_r; ++wi) {
+      uint32_t v = mv_word(m, py, wi);
+      int lo = (wi == wi0) ? b : 0;                       // first bit of interest in this word
+      v = (lo ? (v >> lo) : v);
+      int nbits = 32 - lo;
+      if (in_run) {
+        uint32_t inv = ~v;
+        if (nbits < 32) inv &= (1u << nbits) - 1u;
+        if (inv == 0u) continue;                          // run covers the rest of this word
+        int run = __ffs(inv) - 1;
+        v = (run < 32) ? (v >> run) : 0u;
+        in_run = false;
+      }
+      blocked_r = v != 0u;
+    }
     if (!blocked_r) return false;
   }
   {
@@ -570,6 +613,8 @@ __device__ __forceinline__ void undistort_point(const DevCamera& cam, float sx, 
 }
 
 constexpr int kBlobWarpsPerCta = 4;
+constexpr int kMaxFlagWords = 160;     // row-flag words cached per frame (>= ceil(H/32) * n_ct; 2160-row images with 2 column tiles fit)
+constexpr int kMaxRowsListed = 2176;
 
 struct WarpScratch {
   int cand_x[kCandCap];
@@ -577,9 +622,12 @@ struct WarpScratch {
   int n_cand;
   int n_kept;
   int flags;
+  int n_rows;
   int kept_key[MPE_MAX_BLOBS];     // raster index of the contour start (sort key)
   float kept_cx[MPE_MAX_BLOBS];
   float kept_cy[MPE_MAX_BLOBS];
+  uint32_t rowflags[kMaxFlagWords];
+  uint16_t rows[kMaxRowsListed];   // rows of this frame that contain foreground
 };
 
 __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane) {
@@ -632,53 +680,69 @@ __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Ro
 }
 
 __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(const K1bArgs a) {
-  __shared__ WarpScratch scratch[kBlobWarpsPerCta];
+  extern __shared__ __align__(16) uint8_t k1b_smem[];
+  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(k1b_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kBlobWarpsPerCta + warp;
   if (f >= a.g.n_frames) return;
   WarpScratch& ws = scratch[warp];
   const K1Geom& g = a.g;
   const Roi roi = g.rois ? g.rois[f] : g.roi;
-
-  MaskView m;
-  m.flags = a.rowflags + (size_t)f * g.flags_per_frame;
-  m.mask = a.mask + (size_t)f * g.mask_rows * g.mask_wpr;
-  m.w = roi.w; m.h = roi.h;
-  m.n_ct = g.n_ct;                 // row flags are stored with the launch-wide n_ct stride
-  m.roi_n_ct = (roi.w + g.tw_px - 1) / g.tw_px;
-  m.tw_px = g.tw_px;
-  m.wpr = g.mask_wpr;
-  m.words_per_ct = g.tw_px >> 5;
   const int roi_wpr = (roi.w + 31) >> 5;
-  const int roi_n_ct = m.roi_n_ct;
+  const int roi_n_ct = (roi.w + g.tw_px - 1) / g.tw_px;
   const int roi_strips = (roi.h + kTileRows - 1) / kTileRows;
 
-  if (lane == 0) { ws.n_cand = 0; ws.n_kept = 0; ws.flags = 0; }
+  // ---- cache the row flags of this frame; list the rows that contain foreground (order irrelevant: sorted at the end)
+  if (lane == 0) { ws.n_cand = 0; ws.n_kept = 0; ws.flags = 0; ws.n_rows = 0; }
   __syncwarp();
-
-  // ---- scan the rows that contain foreground, collect contour-start candidates ----
-  for (int s = 0; s < roi_strips; ++s) {
+  const uint32_t* gflags = a.rowflags + (size_t)f * g.flags_per_frame;
+  for (int i = lane; i < roi_strips * g.n_ct && i < kMaxFlagWords; i += 32) ws.rowflags[i] = gflags[i];
+  __syncwarp();
+  for (int s = lane; s < roi_strips; s += 32) {
     uint32_t fl = 0;
-    for (int ct = 0; ct < roi_n_ct; ++ct) fl |= m.flags[s * g.n_ct + ct];
+    for (int ct = 0; ct < roi_n_ct; ++ct) fl |= ws.rowflags[s * g.n_ct + ct];
     while (fl) {
       int r = __ffs(fl) - 1;
       fl &= fl - 1;
-      int y = s * kTileRows + r;
-      for (int wbase = 0; wbase < roi_wpr; wbase += 32) {
-        int wi = wbase + lane;
-        uint32_t cand = (wi < roi_wpr) ? candidate_bits(m, y, wi) : 0u;
-        if (wi == roi_wpr - 1 && (roi.w & 31)) cand &= 0xffffffffu >> (32 - (roi.w & 31));
+      int slot = atomicAdd(&ws.n_rows, 1);
+      if (slot < kMaxRowsListed) ws.rows[slot] = (uint16_t)(s * kTileRows + r);
+    }
+  }
+  __syncwarp();
+
+  MaskView m;
+  m.flags = ws.rowflags;
+  m.mask = a.mask + (size_t)f * g.mask_rows * g.mask_wpr;
+  m.w = roi.w; m.h = roi.h;
+  m.n_ct = g.n_ct;                 // row flags are stored with the launch-wide n_ct stride
+  m.roi_n_ct = roi_n_ct;
+  m.tw_px = g.tw_px;
+  m.wpr = g.mask_wpr;
+  m.words_per_ct = g.tw_px >> 5;
+
+  // ---- contour-start candidates: one lane per foreground row, then lane-parallel border following
+  const int n_rows = min(ws.n_rows, kMaxRowsListed);
+  for (int base = 0; base < n_rows; base += 32) {
+    if (base + lane < n_rows) {
+      const int y = ws.rows[base + lane];
+      // non-zero words of the row first (independent loads), then the neighbourhood test only where needed
+      unsigned long long nz = 0;
+      for (int wi = 0; wi < roi_wpr; ++wi)
+        if (mv_word(m, y, wi)) nz |= 1ull << (wi & 63);
+      for (int wi = 0; wi < roi_wpr; ++wi) {
+        if (roi_wpr <= 64 && !((nz >> wi) & 1ull)) continue;
+        uint32_t cand = candidate_bits(m, y, wi);
         while (cand) {
-          int b = __ffs(cand) - 1;
+          int bbit = __ffs(cand) - 1;
           cand &= cand - 1;
           int slot = atomicAdd(&ws.n_cand, 1);
-          if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + b; ws.cand_y[slot] = y; }
+          if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + bbit; ws.cand_y[slot] = y; }
           else atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
         }
-        __syncwarp();
-        if (ws.n_cand >= 32) process_candidates(m, a, roi, ws, lane);
       }
     }
+    __syncwarp();
+    if (ws.n_cand >= kCandCap / 2) process_candidates(m, a, roi, ws, lane);
   }
   if (ws.n_cand > 0) process_candidates(m, a, roi, ws, lane);
   __syncwarp();
@@ -705,7 +769,14 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
 
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
   int grid = (a.g.n_frames + kBlobWarpsPerCta - 1) / kBlobWarpsPerCta;
-  extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, 0, st>>>(a);
+  static bool configured = false;
+  size_t smem = sizeof(WarpScratch) * kBlobWarpsPerCta;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(extract_blobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, smem, st>>>(a);
   return cudaGetLastError();
 }
 
