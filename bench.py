@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=8192, help="frames per GPU per step")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--leds", type=int, default=N_LEDS)
     ap.add_argument("--width", type=int, default=WIDTH)

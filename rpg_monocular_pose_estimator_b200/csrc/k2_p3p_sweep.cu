@@ -17,7 +17,13 @@
 
 namespace mpe {
 
-constexpr int kK2Threads = 256;
+#ifndef MPE_K2_THREADS
+#define MPE_K2_THREADS 256
+#endif
+#ifndef MPE_K2_MINBLOCKS
+#define MPE_K2_MINBLOCKS 3
+#endif
+constexpr int kK2Threads = MPE_K2_THREADS;
 
 // lexicographic unranking of a 3-combination of {0..n-1}
 __device__ __forceinline__ void unrank_comb3(int n, int idx, int& a, int& b, int& c) {
@@ -93,7 +99,7 @@ __device__ int decode_histogram(uint32_t* hist, int n_det, int n_obj, uint32_t t
   return n;
 }
 
-__global__ void __launch_bounds__(kK2Threads, 2) p3p_sweep_kernel(const K2Args a) {
+__global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel(const K2Args a) {
   __shared__ K2Shared sh;
   const int f = blockIdx.x / a.split;
   const int part = blockIdx.x - f * a.split;

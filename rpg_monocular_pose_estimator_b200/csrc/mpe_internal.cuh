@@ -11,7 +11,7 @@ constexpr int kTileRows = 32;        // output rows per K1 tile (= bits of one r
 constexpr int kMaxRadius = 4;        // largest Gaussian radius the fused kernel is instantiated for
 constexpr int kMaxTaps = 2 * kMaxRadius + 1;
 constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
-constexpr int kK1Threads = 256;
+constexpr int kK1Threads = 512;
 constexpr int kCandCap = 256;        // candidate contour starts buffered per frame-warp in K1b
 
 // Camera model as the kernels consume it.
