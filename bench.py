@@ -299,7 +299,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        names = ["find_leds", "extract_blobs", "p3p_sweep", "validate_refine"]
+        names = ["scan (K1a)", "extract_blobs (K1b)", "p3p_sweep (K2)", "check+refine (K3)", "blur_tiles (K1c)"]
         ksum = sum(kt)
         alg_bytes = B * W * H                                        # ROI bytes read once
         k1_gbs = alg_bytes / (kt[0] * 1e-3) / 1e9 if kt[0] > 0 else 0.0
@@ -309,7 +309,8 @@ def main():
         kernels[0].update({"bound": "hbm", "achieved_gbs": k1_gbs, "frac": k1_gbs / peak})
         kernels[1].update({"bound": "latency (sparse contour tracing)"})
         kernels[2].update({"bound": "fp64 alu", "p3p_solves_per_s": B * 600 / (kt[2] * 1e-3) if kt[2] > 0 and args.leds == 5 else None})
-        kernels[3].update({"bound": "latency (dependent GN chain)"})
+        kernels[3].update({"bound": "fp64 alu / latency (dependent GN chain)"})
+        kernels[4].update({"bound": "latency (sparse exact blur of hot tiles)"})
         line = {
             "metric": "frames/sec (752x480, 5 LEDs, cold full pipeline)" if (W, H, args.leds) == (752, 480, 5) else f"frames/sec ({W}x{H}, {args.leds} LEDs, cold)",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -322,7 +323,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_timed,
-            "roofline": {"kernel": "find_leds (threshold + Gaussian + mask, K1a)", "bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "scan_kernel (K1a: TMA-streamed threshold scan of every ROI byte; findLeds hot loop)", "bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                          "frac": k1_gbs / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kt[0]},
             "dominant_kernel": names[int(np.argmax(kt))],

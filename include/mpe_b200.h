@@ -177,10 +177,11 @@ int mpe_streams_step_device(mpe_ctx* ctx, const uint8_t* frames_device, int pitc
 
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* When enabled, the batch entry points bracket each kernel with CUDA events on the launching stream.
- * mpe_get_kernel_times returns, for the last synchronised batch, milliseconds per kernel:
- * [0] find_leds (threshold+blur+mask), [1] extract_blobs, [2] p3p_sweep, [3] validate_refine. */
+ * mpe_get_kernel_times returns, for the last synchronised batch, milliseconds per stage:
+ * [0] scan (K1a, the streaming pass), [1] extract_blobs (K1b), [2] p3p_sweep (K2), [3] check + refine (K3a+K3b),
+ * [4] blur_tiles (K1c, exact fixed-point blur of the hot tiles). */
 int mpe_enable_kernel_timing(mpe_ctx* ctx, int on);
-int mpe_get_kernel_times(mpe_ctx* ctx, float ms_out[4]);
+int mpe_get_kernel_times(mpe_ctx* ctx, float ms_out[5]);
 /* number of kernel launches issued by this context so far */
 long long mpe_kernel_launch_count(const mpe_ctx* ctx);
 

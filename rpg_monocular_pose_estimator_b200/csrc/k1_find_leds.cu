@@ -127,75 +127,47 @@ __device__ __forceinline__ TileCoord decode_tile(const K1Geom& g, const TileCurs
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1a
+// K1a — scan_kernel: the streaming pass.  Persistent CTAs pull (frame, strip, column-tile) boxes through a TMA ring and
+// only answer "which 32-bit words hold a byte above the threshold".  Tiles without such a word (the vast majority of an
+// LED image) produce no output at all; for the others the CTA appends the word list to a global pool and files a HotTile
+// record.  All exact arithmetic happens in K1c on those few tiles, with far more CTAs per SM than the 100 KB ring allows
+// here — in the first (fused) version the rare slow path stalled the ring: 42 % of the warp stalls were barrier waits and
+// the kernel sat at 0.49 of the HBM roofline.
 // ------------------------------------------------------------------------------------------------
-// Shared-memory layout (dynamic):
-//   [0, 64)                               mbarriers (one per stage)
-//   misc  [4] u32                         [0] #hot units, [1] #active words, [2] row mask of the tile's output
-//   act   [kTileRows][hot_wpr] u32        output words whose source neighbourhood holds a byte > thr   (kept all-zero between tiles)
-//   omask [kTileRows][om_wpr] u32         non-zero bits of the blurred output rows                     (kept all-zero between tiles)
-//   hotu  [rows * box_w / 4] u16          16-byte units that may hold a byte > thr (conservative: OR of the 4 words)
-//   list  [kTileRows * box_w] u16         compacted (row << 8 | word) pairs that need the exact blur
-//   stage ring: kStages x stage_stride bytes (1024-byte aligned start)
-struct K1Smem {
-  uint64_t* bars;
-  uint32_t* misc;
-  uint32_t* act;
-  uint32_t* omask;
-  uint16_t* hotu;
-  uint16_t* list;
-  uint8_t* ring;
-};
+// Shared-memory layout (dynamic):  [0,64) mbarriers | misc[4] u32 | hot[kHotListCap] u16 | ring (1024-byte aligned)
+constexpr int kHotListCap = 1024;        // hot words listed per tile; beyond that the tile is handed over as "dense"
 
-__host__ __device__ inline size_t k1_ring_offset(int rows, int box_w, int tw_px) {
-  int hot_wpr = (box_w + 31) >> 5;
-  int om_wpr = (tw_px + 31) >> 5;
-  size_t off = 64 + (size_t)(4 + kTileRows * hot_wpr + kTileRows * om_wpr) * 4;
-  off += (size_t)(rows * (box_w >> 2)) * 2;       // hotu
-  off = (off + 3) & ~(size_t)3;
-  off += (size_t)kTileRows * box_w * 2;           // list
+__host__ __device__ inline size_t k1_ring_offset() {
+  size_t off = 64 + 16 + (size_t)kHotListCap * 2;
   return (off + 1023) & ~(size_t)1023;
 }
 
 template <int R, bool kLowThr, int kStages>
-__global__ void __launch_bounds__(kK1Threads, 2) find_leds_kernel(const __grid_constant__ CUtensorMap tmap, const K1aArgs a) {
+__global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_constant__ CUtensorMap tmap, const K1aArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const K1Geom& g = a.g;
   constexpr int kRows = kTileRows + 2 * R;
   const int box_w = g.box_w;                       // u32 per smem row
-  const int row_bytes = box_w * 4;
-  const int hot_wpr = (box_w + 31) >> 5;
-  const int om_wpr = (g.tw_px + 31) >> 5;
-  const uint32_t stage_bytes = (uint32_t)(kRows * row_bytes);          // bytes one TMA box delivers
+  const uint32_t stage_bytes = (uint32_t)(kRows * box_w * 4);          // bytes one TMA box delivers
   const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;           // TMA destinations must be 128-byte aligned
   const int units_per_row = box_w >> 2;
   const int n_units = kRows * units_per_row;
 
-  K1Smem sm;
-  sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
-  sm.misc = reinterpret_cast<uint32_t*>(smem_raw + 64);
-  sm.act = sm.misc + 4;
-  sm.omask = sm.act + kTileRows * hot_wpr;
-  sm.hotu = reinterpret_cast<uint16_t*>(sm.omask + kTileRows * om_wpr);
-  {
-    size_t off = (size_t)(reinterpret_cast<uint8_t*>(sm.hotu) - smem_raw) + (size_t)n_units * 2;
-    off = (off + 3) & ~(size_t)3;
-    sm.list = reinterpret_cast<uint16_t*>(smem_raw + off);
-  }
-  sm.ring = smem_raw + k1_ring_offset(kRows, box_w, g.tw_px);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + 64);         // [0] hot words of the current tile, [1] pool offset
+  uint16_t* hot = reinterpret_cast<uint16_t*>(smem_raw + 80);
+  uint8_t* ring = smem_raw + k1_ring_offset();
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
   const int n_tiles = g.n_frames * g.n_strips * g.n_ct;
-
-  for (int i = tid; i < 4 + kTileRows * hot_wpr + kTileRows * om_wpr; i += kK1Threads) sm.misc[i] = 0u;   // misc, act, omask contiguous
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bars[s], 1);
+    misc[0] = 0u; misc[1] = 0u;
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  // producer state (thread 0 only): next tile to look at, number of valid tiles issued so far
+  // producer state (thread 0 only)
   int ptile = blockIdx.x, pstage = 0;
   TileCursor pcur;
   pcur.init(g, blockIdx.x, gridDim.x);
@@ -209,8 +181,8 @@ __global__ void __launch_bounds__(kK1Threads, 2) find_leds_kernel(const __grid_c
       pstage = (pstage + 1 == kStages) ? 0 : pstage + 1;
       int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
       int y0 = c.roi.y + c.s * kTileRows - R;
-      mbar_expect_tx(&sm.bars[stage], stage_bytes);
-      tma_load_3d(sm.ring + (size_t)stage * stage_stride, &tmap, &sm.bars[stage], x_elem0, y0, c.f);
+      mbar_expect_tx(&bars[stage], stage_bytes);
+      tma_load_3d(ring + (size_t)stage * stage_stride, &tmap, &bars[stage], x_elem0, y0, c.f);
       return;
     }
   };
@@ -218,8 +190,19 @@ __global__ void __launch_bounds__(kK1Threads, 2) find_leds_kernel(const __grid_c
     for (int s = 0; s < kStages; ++s) produce_one();
 
   const uint32_t thr_k = (uint32_t)a.thr_k;
+  auto push_unit = [&](int u, const uint4& v) {     // exact per-word test of one 16-byte unit
+    const int row = u / units_per_row;
+    const int w0 = (u - row * units_per_row) * 4;
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (any_byte_gt<kLowThr>(wv[q], thr_k)) {
+        uint32_t slot = atomicAdd(&misc[0], 1u);
+        if (slot < (uint32_t)kHotListCap) hot[slot] = (uint16_t)((row << 8) | (w0 + q));
+      }
+  };
 
-  int cstage = 0;            // ring slot and phase parity of the next valid tile this CTA consumes
+  int cstage = 0;
   uint32_t cparity = 0;
   TileCursor ccur;
   ccur.init(g, blockIdx.x, gridDim.x);
@@ -229,12 +212,11 @@ __global__ void __launch_bounds__(kK1Threads, 2) find_leds_kernel(const __grid_c
     const int stage = cstage;
     const uint32_t parity = cparity;
     if (++cstage == kStages) { cstage = 0; cparity ^= 1u; }
-    mbar_wait(&sm.bars[stage], parity);
-    const uint8_t* tile_smem = sm.ring + (size_t)stage * stage_stride;
-    const uint4* units = reinterpret_cast<const uint4*>(tile_smem);
+    mbar_wait(&bars[stage], parity);
+    const uint4* units = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_stride);
 
-    // ---------------- dense phase: which 16-byte units may hold a byte above the threshold? ----------------
-    // four units (64 bytes) per test: OR all sixteen words, one SWAR compare; split up only when that is positive
+    // four 16-byte units (64 bytes) per test: OR the sixteen words, one SWAR compare; split up only when it is positive
+    int pushed = 0;
     for (int base = 0; base < n_units; base += 4 * kK1Threads) {
       const int u0 = base + tid;
       uint4 v0 = (u0 < n_units) ? units[u0] : make_uint4(0, 0, 0, 0);
@@ -244,151 +226,204 @@ __global__ void __launch_bounds__(kK1Threads, 2) find_leds_kernel(const __grid_c
       uint32_t o0 = (v0.x | v0.y) | (v0.z | v0.w), o1 = (v1.x | v1.y) | (v1.z | v1.w);
       uint32_t o2 = (v2.x | v2.y) | (v2.z | v2.w), o3 = (v3.x | v3.y) | (v3.z | v3.w);
       if (any_byte_gt<kLowThr>((o0 | o1) | (o2 | o3), thr_k)) {
-        if (any_byte_gt<kLowThr>(o0, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)u0;
-        if (any_byte_gt<kLowThr>(o1, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + kK1Threads);
-        if (any_byte_gt<kLowThr>(o2, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + 2 * kK1Threads);
-        if (any_byte_gt<kLowThr>(o3, thr_k)) sm.hotu[atomicAdd(&sm.misc[0], 1u)] = (uint16_t)(u0 + 3 * kK1Threads);
+        pushed = 1;
+        if (any_byte_gt<kLowThr>(o0, thr_k)) push_unit(u0, v0);
+        if (any_byte_gt<kLowThr>(o1, thr_k)) push_unit(u0 + kK1Threads, v1);
+        if (any_byte_gt<kLowThr>(o2, thr_k)) push_unit(u0 + 2 * kK1Threads, v2);
+        if (any_byte_gt<kLowThr>(o3, thr_k)) push_unit(u0 + 3 * kK1Threads, v3);
+      }
+    }
+    // one barrier per tile: all reads of this stage are done, and the hot/cold decision is block-uniform (a thread that
+    // races ahead into the next tile may already be pushing, so the shared counter itself must not be used to decide)
+    if (__syncthreads_or(pushed)) {
+      if (tid == 0) {
+        const uint32_t n_hot = misc[0];
+        uint32_t off = 0xffffffffu;                  // dense hand-over unless the list fits
+        if (n_hot != 0u && n_hot <= (uint32_t)kHotListCap) {
+          uint32_t o = atomicAdd(&a.counters[1], n_hot);
+          if (o + n_hot <= a.pool_capacity) off = o;
+        }
+        misc[1] = off;
+        misc[2] = n_hot;
+        if (n_hot != 0u) {
+          uint32_t rec = atomicAdd(&a.counters[0], 1u);
+          a.hot_tiles[rec] = make_uint4((uint32_t)tile, (off == 0xffffffffu) ? 0xffffffffu : n_hot, off, 0u);
+        }
+      }
+      __syncthreads();
+      const uint32_t off = misc[1], n_hot = misc[2];
+      if (off != 0xffffffffu)
+        for (uint32_t i = tid; i < n_hot; i += kK1Threads) a.pool[off + i] = hot[i];
+      __syncthreads();
+      if (tid == 0) misc[0] = 0u;
+      __syncthreads();
+    }
+    if (tid == 0) produce_one();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c — blur_kernel: exact threshold + fixed-point Gaussian on the hot tiles only, reading the few source pixels it
+// needs straight from global memory (about 1 % of the frame bytes), and writing the 1-bit foreground rows + row flags.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlurThreads = 128;
+
+__device__ __forceinline__ int blur_smem_words(int box_w, int tw_px) {
+  return 4 + kTileRows * ((box_w + 31) >> 5) + kTileRows * ((tw_px + 31) >> 5);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  const K1Geom& g = a.g;
+  const int box_w = g.box_w;
+  const int hot_wpr = (box_w + 31) >> 5;
+  const int om_wpr = (g.tw_px + 31) >> 5;
+  uint32_t* misc = reinterpret_cast<uint32_t*>(bsm);                  // [1] #active words, [2] row mask
+  uint32_t* act = misc + 4;                                            // [kTileRows][hot_wpr]   kept all-zero between tiles
+  uint32_t* omask = act + kTileRows * hot_wpr;                         // [kTileRows][om_wpr]    kept all-zero between tiles
+  uint16_t* list = reinterpret_cast<uint16_t*>(omask + kTileRows * om_wpr);   // [kTileRows * box_w]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < blur_smem_words(box_w, g.tw_px); i += kBlurThreads) misc[i] = 0u;
+  __syncthreads();
+  const uint32_t n_hot_tiles = a.counters[0];
+  const uint32_t thr = (uint32_t)a.threshold;
+  const int per_frame = g.n_strips * g.n_ct;
+
+  for (uint32_t ht = blockIdx.x; ht < n_hot_tiles; ht += gridDim.x) {
+    const uint4 rec = a.hot_tiles[ht];
+    const int tile = (int)rec.x;
+    TileCoord c;
+    c.f = tile / per_frame;
+    { int rem = tile - c.f * per_frame; c.s = rem / g.n_ct; c.ct = rem - c.s * g.n_ct; }
+    c.roi = g.rois ? g.rois[c.f] : g.roi;
+    const int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
+    const int y0 = c.roi.y + c.s * kTileRows - R;
+    const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
+    const int tile_x0 = c.roi.x + c.ct * g.tw_px;                      // output pixel range of this tile
+    const int tile_x1 = min(c.roi.x + c.roi.w, tile_x0 + g.tw_px);
+    const uint8_t* frame = a.frames + (size_t)c.f * a.frame_stride;
+
+    // (B) every hot source word marks the output words it can influence: rows row-2R..row, words j-1..j+1
+    if (rec.y == 0xffffffffu) {                      // dense hand-over: every word of the tile is a candidate
+      for (int item = tid; item < out_rows * hot_wpr; item += kBlurThreads) {
+        int hw = item % hot_wpr;
+        int nb = min(32, box_w - hw * 32);
+        act[item] = (nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u);
+      }
+    } else {
+      for (uint32_t t = tid; t < rec.y; t += kBlurThreads) {
+        const uint32_t e = a.pool[rec.z + t];
+        const int row = (int)(e >> 8), j = (int)(e & 0xff);
+        const int r_lo = max(row - 2 * R, 0), r_hi = min(row, out_rows - 1);
+        for (int jj = max(j - 1, 0); jj <= min(j + 1, box_w - 1); ++jj) {
+          const uint32_t bit = 1u << (jj & 31);
+          for (int r = r_lo; r <= r_hi; ++r) atomicOr(&act[r * hot_wpr + (jj >> 5)], bit);
+        }
       }
     }
     __syncthreads();
-    const int n_hot = (int)sm.misc[0];
-    uint32_t* flag_ptr = a.rowflags + (size_t)c.f * g.flags_per_frame + c.s * g.n_ct + c.ct;
-
-    if (n_hot == 0) {
-      if (tid == 0) *flag_ptr = 0u;
-    } else {
-      // ---------------- sparse phase ----------------
-      const int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
-      const int y0 = c.roi.y + c.s * kTileRows - R;
-      const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
-      // (B) exact per-word test of the hot units; every hot source word marks the output words it can influence:
-      //     output rows row-2R .. row, words j-1 .. j+1
-      for (int t = tid; t < n_hot; t += kK1Threads) {
-        const int u = sm.hotu[t];
-        const uint4 v = units[u];
-        const int row = u / units_per_row;
-        const int w0 = (u - row * units_per_row) * 4;
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    // (C) compact the marked words; the bitmap is cleared on the way
+    for (int item = tid; item < out_rows * hot_wpr; item += kBlurThreads) {
+      uint32_t d = act[item];
+      if (!d) continue;
+      act[item] = 0u;
+      const int r = item / hot_wpr, hw = item - r * hot_wpr;
+      while (d) {
+        const int bit = __ffs(d) - 1;
+        d &= d - 1;
+        list[atomicAdd(&misc[1], 1u)] = (uint16_t)((r << 8) | (hw * 32 + bit));
+      }
+    }
+    __syncthreads();
+    const int n_list = (int)misc[1];
+    // (D) exact arithmetic: cv::threshold(THRESH_TOZERO) -> 8.8 horizontal pass -> 16.16 vertical pass -> round, != 0 ?
+    for (int e = tid; e < n_list; e += kBlurThreads) {
+      const int r = list[e] >> 8, j = list[e] & 0xff;
+      const int first_px = 4 * x_elem0 + 4 * j;                        // image x of the word's first pixel
+      if (first_px + 3 < tile_x0 || first_px >= tile_x1) continue;
+      const int Y = y0 + R + r;                                        // image row of this output row
+      const bool interior = (first_px - R >= c.roi.x) && (first_px + 3 + R < c.roi.x + c.roi.w) &&
+                            (Y - R >= c.roi.y) && (Y + R < c.roi.y + c.roi.h);
+      uint32_t hsum[2 * R + 1][4];
+#pragma unroll
+      for (int dr = 0; dr <= 2 * R; ++dr) {
+        uint32_t px[4 + 2 * R];
+        if (interior) {
+          const uint8_t* src = frame + (size_t)(Y + dr - R) * a.pitch + (first_px - R);
+#pragma unroll
+          for (int k = 0; k < 4 + 2 * R; ++k) px[k] = __ldg(src + k);
+        } else {
+          const int yy = c.roi.y + reflect101(Y + dr - R - c.roi.y, c.roi.h);
+          const uint8_t* srow = frame + (size_t)yy * a.pitch;
+#pragma unroll
+          for (int k = 0; k < 4 + 2 * R; ++k) {
+            const int xx = c.roi.x + reflect101(first_px + k - R - c.roi.x, c.roi.w);
+            px[k] = __ldg(srow + xx);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4 + 2 * R; ++k) px[k] = (px[k] > thr) ? px[k] : 0u;      // strict >
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (!any_byte_gt<kLowThr>(wv[q], thr_k)) continue;
-          const int j = w0 + q;
-          const int r_lo = max(row - 2 * R, 0), r_hi = min(row, out_rows - 1);
-          for (int jj = max(j - 1, 0); jj <= min(j + 1, box_w - 1); ++jj) {
-            const uint32_t bit = 1u << (jj & 31);
-            for (int r = r_lo; r <= r_hi; ++r) atomicOr(&sm.act[r * hot_wpr + (jj >> 5)], bit);
-          }
-        }
-      }
-      __syncthreads();
-      // (C) compact the marked words into a list; the bitmap is cleared on the way (stays clean for the next tile)
-      for (int item = tid; item < out_rows * hot_wpr; item += kK1Threads) {
-        uint32_t d = sm.act[item];
-        if (!d) continue;
-        sm.act[item] = 0u;
-        const int r = item / hot_wpr, hw = item - r * hot_wpr;
-        while (d) {
-          const int bit = __ffs(d) - 1;
-          d &= d - 1;
-          sm.list[atomicAdd(&sm.misc[1], 1u)] = (uint16_t)((r << 8) | (hw * 32 + bit));
-        }
-      }
-      __syncthreads();
-      const int n_list = (int)sm.misc[1];
-      const int tile_x0 = c.roi.x + c.ct * g.tw_px;                      // output pixel range of this tile
-      const int tile_x1 = min(c.roi.x + c.roi.w, tile_x0 + g.tw_px);
-      const uint32_t thr = (uint32_t)a.threshold;
-      // (D) exact fixed-point blur of the listed words (4 output pixels each)
-      for (int e = tid; e < n_list; e += kK1Threads) {
-        const int r = sm.list[e] >> 8, j = sm.list[e] & 0xff;
-        const int first_px = 4 * x_elem0 + 4 * j;                        // image x of the word's first pixel
-        if (first_px + 3 < tile_x0 || first_px >= tile_x1) continue;
-        const int Y = y0 + R + r;                                        // image row of this output row
-        const bool interior = (first_px - R >= c.roi.x) && (first_px + 3 + R < c.roi.x + c.roi.w) &&
-                              (Y - R >= c.roi.y) && (Y + R < c.roi.y + c.roi.h);
-        uint32_t hsum[2 * R + 1][4];                                     // horizontal pass, 8.8 fixed point
-#pragma unroll
-        for (int dr = 0; dr <= 2 * R; ++dr) {
-          uint32_t px[4 + 2 * R];
-          if (interior) {
-            const uint8_t* src = tile_smem + (size_t)(r + dr) * row_bytes + (4 * j - R);
-#pragma unroll
-            for (int k = 0; k < 4 + 2 * R; ++k) px[k] = src[k];
-          } else {
-            int yy = c.roi.y + reflect101(Y + dr - R - c.roi.y, c.roi.h);
-            const uint8_t* srow = tile_smem + (size_t)(yy - y0) * row_bytes;
-#pragma unroll
-            for (int k = 0; k < 4 + 2 * R; ++k) {
-              int xx = c.roi.x + reflect101(first_px + k - R - c.roi.x, c.roi.w);
-              px[k] = srow[xx - 4 * x_elem0];
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 4 + 2 * R; ++k) px[k] = (px[k] > thr) ? px[k] : 0u;      // cv::THRESH_TOZERO, strict >
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k <= 2 * R; ++k) acc += a.taps[k] * px[q + k];
-            hsum[dr][q] = acc;
-          }
-        }
-        uint32_t bits = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int X = first_px + q;
           uint32_t acc = 0;
 #pragma unroll
-          for (int dr = 0; dr <= 2 * R; ++dr) acc += a.taps[dr] * hsum[dr][q];
-          if (X >= tile_x0 && X < tile_x1 && ((acc + 32768u) >> 16)) bits |= 1u << q;     // 16.16 -> u8 round-half-up, non-zero?
+          for (int k = 0; k <= 2 * R; ++k) acc += a.taps[k] * px[q + k];
+          hsum[dr][q] = acc;
         }
-        if (bits) {
+      }
+      uint32_t bits = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (bits & (1u << q)) {
-              int bx = first_px + q - tile_x0;
-              atomicOr(&sm.omask[r * om_wpr + (bx >> 5)], 1u << (bx & 31));
-            }
-          atomicOr(&sm.misc[2], 1u << r);
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int X = first_px + q;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int dr = 0; dr <= 2 * R; ++dr) acc += a.taps[dr] * hsum[dr][q];
+        if (X >= tile_x0 && X < tile_x1 && ((acc + 32768u) >> 16)) bits |= 1u << q;
       }
-      __syncthreads();
-      // (E) write-out of the rows that contain foreground; rows without foreground are not written (flag bit 0)
-      const uint32_t rowmask = sm.misc[2];
-      __syncthreads();
-      if (tid == 0) {
-        *flag_ptr = rowmask;
-        sm.misc[0] = 0u; sm.misc[1] = 0u; sm.misc[2] = 0u;
+      if (bits) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (bits & (1u << q)) {
+            const int bx = first_px + q - tile_x0;
+            atomicOr(&omask[r * om_wpr + (bx >> 5)], 1u << (bx & 31));
+          }
+        atomicOr(&misc[2], 1u << r);
       }
-      const int words_per_ct = g.tw_px >> 5;   // only used when n_ct > 1 (tw_px is a multiple of 32 then)
-      uint32_t rm = rowmask & (0x01010101u << (warp & 7));    // warp w copies the rows r with (r & 7) == (w & 7)
-      if (warp >= 8) rm = 0u;
-      while (rm) {
-        const int r = __ffs(rm) - 1;
-        rm &= rm - 1;
-        uint32_t* dst = a.mask + ((size_t)c.f * g.mask_rows + (c.s * kTileRows + r)) * g.mask_wpr + c.ct * words_per_ct;
-        for (int w = lane; w < om_wpr; w += 32) {
-          dst[w] = sm.omask[r * om_wpr + w];
-          sm.omask[r * om_wpr + w] = 0u;
-        }
-      }
-      __syncthreads();
     }
-    // every thread is past a barrier that follows its last read of this stage: refill it
-    if (tid == 0) produce_one();
+    __syncthreads();
+    // (E) rows with foreground go to the global mask; rows without are not written (their flag bit stays 0)
+    const uint32_t rowmask = misc[2];
+    __syncthreads();
+    if (tid == 0) {
+      a.rowflags[(size_t)c.f * g.flags_per_frame + c.s * g.n_ct + c.ct] = rowmask;
+      misc[1] = 0u; misc[2] = 0u;
+    }
+    const int words_per_ct = g.tw_px >> 5;   // only used when n_ct > 1 (tw_px is a multiple of 32 then)
+    uint32_t rm = rowmask & (0x11111111u << warp);                     // 4 warps: warp w copies rows r with (r & 3) == w
+    while (rm) {
+      const int r = __ffs(rm) - 1;
+      rm &= rm - 1;
+      uint32_t* dst = a.mask + ((size_t)c.f * g.mask_rows + (c.s * kTileRows + r)) * g.mask_wpr + c.ct * words_per_ct;
+      for (int w = lane; w < om_wpr; w += 32) {
+        dst[w] = omask[r * om_wpr + w];
+        omask[r * om_wpr + w] = 0u;
+      }
+    }
+    __syncthreads();
   }
 }
 
 size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages) {
   int rows = kTileRows + 2 * radius;
   size_t stage_stride = ((size_t)rows * g.box_w * 4 + 127) & ~(size_t)127;
-  return k1_ring_offset(rows, g.box_w, g.tw_px) + (size_t)stages * stage_stride;
+  return k1_ring_offset() + (size_t)stages * stage_stride;
 }
 
 template <int R, bool kLow, int kStages>
-static cudaError_t launch_k1a_inst(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
+static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
   size_t smem = find_leds_smem_bytes(a.g, R, kStages);
-  auto kern = find_leds_kernel<R, kLow, kStages>;
+  auto kern = scan_kernel<R, kLow, kStages>;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -404,21 +439,42 @@ static cudaError_t launch_k1a_inst(const K1aArgs& a, const CUtensorMap& tmap, in
 }
 
 template <int R>
-static cudaError_t launch_k1a_r(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
-  // stage count: as many as fit in ~105 KB so that two CTAs share an SM
+static cudaError_t launch_k1_r(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
+  // ring depth: as many stages as fit in ~110 KB so that two CTAs share an SM
   size_t s4 = find_leds_smem_bytes(a.g, R, 4), s3 = find_leds_smem_bytes(a.g, R, 3);
   bool low = a.threshold < 128;
-  if (s4 <= 110 * 1024) return low ? launch_k1a_inst<R, true, 4>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 4>(a, tmap, n_sms, st);
-  if (s3 <= 110 * 1024) return low ? launch_k1a_inst<R, true, 3>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 3>(a, tmap, n_sms, st);
-  return low ? launch_k1a_inst<R, true, 2>(a, tmap, n_sms, st) : launch_k1a_inst<R, false, 2>(a, tmap, n_sms, st);
+  cudaError_t e;
+  if (s4 <= 110 * 1024) e = low ? launch_scan_inst<R, true, 4>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 4>(a, tmap, n_sms, st);
+  else if (s3 <= 110 * 1024) e = low ? launch_scan_inst<R, true, 3>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 3>(a, tmap, n_sms, st);
+  else e = low ? launch_scan_inst<R, true, 2>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 2>(a, tmap, n_sms, st);
+  return e;
+}
+
+template <int R>
+static cudaError_t launch_blur_r(const K1aArgs& a, int n_sms, cudaStream_t st) {
+  size_t bsmem = (size_t)(4 + kTileRows * ((a.g.box_w + 31) >> 5) + kTileRows * ((a.g.tw_px + 31) >> 5)) * 4 + (size_t)kTileRows * a.g.box_w * 2;
+  int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
+  int grid = n_tiles < n_sms * 8 ? n_tiles : n_sms * 8;
+  blur_kernel<R><<<grid, kBlurThreads, bsmem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st) {
+  switch (radius) {
+    case 1: return launch_blur_r<1>(a, n_sms, st);
+    case 2: return launch_blur_r<2>(a, n_sms, st);
+    case 3: return launch_blur_r<3>(a, n_sms, st);
+    case 4: return launch_blur_r<4>(a, n_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st) {
   switch (radius) {
-    case 1: return launch_k1a_r<1>(a, tmap, n_sms, st);
-    case 2: return launch_k1a_r<2>(a, tmap, n_sms, st);
-    case 3: return launch_k1a_r<3>(a, tmap, n_sms, st);
-    case 4: return launch_k1a_r<4>(a, tmap, n_sms, st);
+    case 1: return launch_k1_r<1>(a, tmap, n_sms, st);
+    case 2: return launch_k1_r<2>(a, tmap, n_sms, st);
+    case 3: return launch_k1_r<3>(a, tmap, n_sms, st);
+    case 4: return launch_k1_r<4>(a, tmap, n_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }

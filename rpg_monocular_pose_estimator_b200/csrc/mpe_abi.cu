@@ -18,6 +18,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+constexpr size_t kPoolPerFrame = 1024;   // hot-word pool entries reserved per frame of capacity (overflow degrades to the dense path)
+
 struct DevBuffers {
   uint8_t* frames = nullptr;       // [max_batch][max_h][pitch]
   uint32_t* rowflags = nullptr;    // [max_batch][flags_per_frame]
@@ -38,6 +40,9 @@ struct DevBuffers {
   Roi* rois = nullptr;             // [max_batch]
   mpe_result* results = nullptr;   // [max_batch]
   double* check_sums = nullptr;    // [max_batch][MPE_MAX_LEDS*3]
+  uint4* hot_tiles = nullptr;      // [max_batch * flags_per_frame]
+  uint16_t* pool = nullptr;        // [max_batch * kPoolPerFrame]
+  uint32_t* counters = nullptr;    // [2]
   int* check_cnt = nullptr;        // [max_batch][2]
 };
 
@@ -59,8 +64,7 @@ struct mpe_ctx {
   mpe_params params{};
   // instrumentation
   bool timing = false;
-  cudaEvent_t ev[8]{};
-  float kernel_ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[10]{};
   bool timing_pending = false;
   long long launches = 0;
   std::string err;
@@ -206,10 +210,22 @@ int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, 
   a.thr_k = (T < 128) ? (127 - T) * 0x01010101 : (255 - T) * 0x01010101;
   a.rowflags = c->d.rowflags + (size_t)slot0 * c->flags_per_frame;
   a.mask = c->d.mask + (size_t)slot0 * c->max_h * c->mask_wpr;
+  a.hot_tiles = c->d.hot_tiles + (size_t)slot0 * c->flags_per_frame;
+  a.pool = c->d.pool + (size_t)slot0 * kPoolPerFrame;
+  a.pool_capacity = (uint32_t)((size_t)n * kPoolPerFrame);
+  a.counters = c->d.counters;
+  a.frames = sub.base;
+  a.pitch = src.pitch;
+  a.frame_stride = src.frame_stride;
+  CUDA_TRY(c, cudaMemsetAsync(a.rowflags, 0, (size_t)n * c->flags_per_frame * sizeof(uint32_t), st));
+  CUDA_TRY(c, cudaMemsetAsync(a.counters, 0, 2 * sizeof(uint32_t), st));
   time_begin(c, 0, st);
   CUDA_TRY(c, launch_find_leds(a, tmap, radius, c->n_sms, st));
   time_end(c, 0, st);
-  ++c->launches;
+  time_begin(c, 4, st);
+  CUDA_TRY(c, launch_blur_tiles(a, radius, c->n_sms, st));
+  time_end(c, 4, st);
+  c->launches += 2;
 
   K1bArgs b{};
   b.g = a.g;
@@ -402,12 +418,15 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.results, B));
   CREATE_TRY(dev_alloc(&c->d.check_sums, B * MPE_MAX_LEDS * 3));
   CREATE_TRY(dev_alloc(&c->d.check_cnt, B * 2));
+  CREATE_TRY(dev_alloc(&c->d.hot_tiles, B * c->flags_per_frame));
+  CREATE_TRY(dev_alloc(&c->d.pool, B * kPoolPerFrame));
+  CREATE_TRY(dev_alloc(&c->d.counters, 2));
   CREATE_TRY(cudaMemset(c->d.n_corr, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.flags, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.corr, 0, B * 2 * MPE_MAX_LEDS * sizeof(uint32_t)));
   CREATE_TRY(cudaMemset(c->d.rowflags, 0, B * c->flags_per_frame * sizeof(uint32_t)));
   CREATE_TRY(cudaMallocHost((void**)&c->h_results, B * sizeof(mpe_result)));
-  for (int i = 0; i < 8; ++i) CREATE_TRY(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 10; ++i) CREATE_TRY(cudaEventCreate(&c->ev[i]));
   // PoseEstimator::PoseEstimator() defaults (pose_estimator.cpp:36-39)
   c->pp.back_projection_pixel_tolerance = 3;
   c->pp.back_proj_sq_max = sqrt_less_than_bound(3.0);
@@ -430,9 +449,9 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
   cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.done); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
-  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters);
   if (c->h_results) cudaFreeHost(c->h_results);
-  for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -725,11 +744,11 @@ int mpe_streams_step_device(mpe_ctx* c, const uint8_t*, int, long long, int, int
 
 int mpe_enable_kernel_timing(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->timing = on != 0; return MPE_OK; }
 
-int mpe_get_kernel_times(mpe_ctx* c, float ms_out[4]) {
+int mpe_get_kernel_times(mpe_ctx* c, float ms_out[5]) {
   if (!c || !ms_out) return MPE_E_INVALID;
   if (!c->timing || !c->timing_pending) return fail(c, MPE_E_INVALID, "kernel timing not enabled or no batch run yet");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     CUDA_TRY(c, cudaEventSynchronize(c->ev[2 * k + 1]));
     CUDA_TRY(c, cudaEventElapsedTime(&ms_out[k], c->ev[2 * k], c->ev[2 * k + 1]));
   }

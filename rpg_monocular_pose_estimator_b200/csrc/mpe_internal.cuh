@@ -11,7 +11,7 @@ constexpr int kTileRows = 32;        // output rows per K1 tile (= bits of one r
 constexpr int kMaxRadius = 4;        // largest Gaussian radius the fused kernel is instantiated for
 constexpr int kMaxTaps = 2 * kMaxRadius + 1;
 constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
-constexpr int kK1Threads = 512;
+constexpr int kK1Threads = 256;
 constexpr int kCandCap = 256;        // candidate contour starts buffered per frame-warp in K1b
 
 // Camera model as the kernels consume it.
@@ -58,8 +58,16 @@ struct K1aArgs {
   int thr_k;                 // SWAR constant for "any byte > threshold"
   int threshold;
   uint32_t taps[kMaxTaps];   // 8.8 fixed-point Gaussian taps, sum = 256
-  uint32_t* rowflags;        // [n_frames][flags_per_frame]
+  uint32_t* rowflags;        // [n_frames][flags_per_frame]   zeroed before the launch; K1c writes the hot tiles' words
   uint32_t* mask;            // [n_frames][mask_rows][mask_wpr]
+  // K1a -> K1c hand-over
+  uint4* hot_tiles;          // [n_tiles] records {tile id, #hot words (0xffffffff = dense), pool offset, -}
+  uint16_t* pool;            // hot words (row << 8 | word) of all hot tiles
+  uint32_t pool_capacity;
+  uint32_t* counters;        // [0] #hot tiles, [1] pool fill; zeroed before the launch
+  const uint8_t* frames;     // frame 0 of this launch (device), for K1c's direct pixel reads
+  int pitch;
+  long long frame_stride;
 };
 
 struct K1bArgs {
@@ -113,6 +121,7 @@ struct K3Args {
 
 // ---- launchers (defined next to the kernels) ----
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
+cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);
 cudaError_t launch_p3p_sweep(const K2Args& a, cudaStream_t st);
 cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st);

@@ -151,7 +151,7 @@ class Context:
         self.check(self.L.mpe_enable_kernel_timing(self.h, 1 if on else 0))
 
     def kernel_times_ms(self):
-        out = (C.c_float * 4)()
+        out = (C.c_float * 5)()
         self.check(self.L.mpe_get_kernel_times(self.h, out))
         return list(out)
 
