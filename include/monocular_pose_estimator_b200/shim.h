@@ -1,0 +1,461 @@
+// Header-only C++ shim: re-creates the class API of monocular_pose_estimator_lib (LEDDetector, PoseEstimator) on top
+// of the C ABI in mpe_b200.h, so that the reference's callers (MPENode: monocular_pose_estimator/src/
+// monocular_pose_estimator.cpp:84,110-120,159,163-164,222-233; the nodelet wraps MPENode) compile against it unchanged.
+//
+//   * With Eigen and OpenCV headers available the reference's own typedefs are used (datatypes.h:38-52, cv::Mat, ...).
+//   * Without them (this build image has neither) minimal stand-ins with the same member syntax are used, so the shim can
+//     still be compiled and exercised (tests/cpp/shim_demo.cpp); define MPE_SHIM_FORCE_STANDIN to force that mode.
+//
+// The heavy stages are the CUDA kernels behind mpe_find_leds / mpe_initialise / mpe_check_correspondences /
+// mpe_optimise_pose; the state machine (estimateBodyPose, pose_estimator.cpp:62-147) and the tiny sequential helpers of
+// tracking mode (predictPose, determineROI, findCorrespondences) stay on the host exactly as in the reference.
+#ifndef MPE_B200_SHIM_H_
+#define MPE_B200_SHIM_H_
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../mpe_b200.h"
+
+#if !defined(MPE_SHIM_FORCE_STANDIN) && defined(__has_include)
+#if __has_include(<Eigen/Dense>) && __has_include(<opencv2/core.hpp>)
+#define MPE_SHIM_REAL_TYPES 1
+#endif
+#endif
+
+#ifdef MPE_SHIM_REAL_TYPES
+#include <Eigen/Dense>
+#include <opencv2/core.hpp>
+namespace monocular_pose_estimator {
+typedef Eigen::Matrix<double, 6, 6> Matrix6d;
+typedef Eigen::Matrix<unsigned, Eigen::Dynamic, 2> VectorXuPairs;
+typedef Eigen::Matrix<Eigen::Vector2d, Eigen::Dynamic, 1> List2DPoints;
+typedef Eigen::Matrix<Eigen::Vector4d, Eigen::Dynamic, 1> List4DPoints;
+typedef Eigen::Matrix4d Matrix4dT;
+typedef cv::Mat ImageT;
+typedef cv::Mat CameraMatT;
+typedef cv::Rect RectT;
+typedef cv::Size SizeT;
+typedef cv::Point2f Point2fT;
+inline double cam_at(const CameraMatT& K, int r, int c) { return K.at<double>(r, c); }
+}  // namespace monocular_pose_estimator
+#else
+namespace monocular_pose_estimator {
+namespace standin {
+template <int N> struct Vec {
+  double v[N];
+  Vec() { for (int i = 0; i < N; ++i) v[i] = 0; }
+  double& operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+};
+template <typename T> struct List {
+  std::vector<T> d;
+  size_t size() const { return d.size(); }
+  void resize(size_t n) { d.resize(n); }
+  T& operator()(size_t i) { return d[i]; }
+  const T& operator()(size_t i) const { return d[i]; }
+};
+template <int R, int C> struct Mat {   // column-major like Eigen
+  double m[R * C];
+  Mat() { for (int i = 0; i < R * C; ++i) m[i] = 0; }
+  double& operator()(int r, int c) { return m[c * R + r]; }
+  double operator()(int r, int c) const { return m[c * R + r]; }
+};
+struct Pairs {
+  std::vector<unsigned> d; int n = 0;
+  int rows() const { return n; }
+  void resize(int r, int) { n = r; d.assign((size_t)r * 2, 0u); }
+  unsigned& operator()(int r, int c) { return d[(size_t)r * 2 + c]; }
+  unsigned operator()(int r, int c) const { return d[(size_t)r * 2 + c]; }
+};
+struct Image { const uint8_t* data = nullptr; int rows = 0, cols = 0; size_t step = 0; };
+struct Camera { double k[9]; };   // row-major 3x3
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+}  // namespace standin
+typedef standin::Mat<6, 6> Matrix6d;
+typedef standin::Pairs VectorXuPairs;
+typedef standin::List<standin::Vec<2> > List2DPoints;
+typedef standin::List<standin::Vec<4> > List4DPoints;
+typedef standin::Mat<4, 4> Matrix4dT;
+typedef standin::Image ImageT;
+typedef standin::Camera CameraMatT;
+typedef standin::Rect RectT;
+typedef standin::Size SizeT;
+typedef standin::Point2f Point2fT;
+inline double cam_at(const CameraMatT& K, int r, int c) { return K.k[3 * r + c]; }
+}  // namespace monocular_pose_estimator
+#endif
+
+namespace monocular_pose_estimator {
+
+namespace detail {
+inline void check(mpe_ctx* c, int rc, const char* what) {
+  if (rc != MPE_OK) throw std::runtime_error(std::string(what) + ": " + (c ? mpe_last_error(c) : "no context"));
+}
+inline void camera_to_rowmajor(const CameraMatT& K, double out[9]) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[3 * r + c] = cam_at(K, r, c);
+}
+// small row-major 4x4 helpers for the host-side tracking math
+inline void mul44(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j]; C[4 * i + j] = s; }
+}
+inline void rigid_inverse(const double* T, double* Ti) {   // general inverse of [R t; 0 1] through the 3x3 adjugate
+  const double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];
+  const double A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
+  const double det = a * A + b * B + c * Cc, id = 1.0 / det;
+  double Ri[9] = {A * id, -(b * i - c * h) * id, (b * f - c * e) * id, B * id, (a * i - c * g) * id, -(a * f - c * d) * id,
+                  Cc * id, -(a * h - b * g) * id, (a * e - b * d) * id};
+  for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) Ti[4 * r + cc] = Ri[3 * r + cc]; Ti[4 * r + 3] = -(Ri[3 * r] * T[3] + Ri[3 * r + 1] * T[7] + Ri[3 * r + 2] * T[11]); }
+  Ti[12] = Ti[13] = Ti[14] = 0; Ti[15] = 1;
+}
+}  // namespace detail
+
+class LEDDetector {
+ public:
+  // led_detector.h:84-88.  Uses (and lazily creates) a process-wide context sized for the image; the PoseEstimator
+  // shim below uses its own context instead.
+  static void findLeds(const ImageT& image, RectT ROI, const int& threshold_value, const double& gaussian_sigma, const double& min_blob_area,
+                       const double& max_blob_area, const double& max_width_height_distortion, const double& max_circular_distortion,
+                       List2DPoints& pixel_positions, std::vector<Point2fT>& distorted_detection_centers, const CameraMatT& camera_matrix_K,
+                       const std::vector<double>& camera_distortion_coeffs) {
+    mpe_ctx* ctx = defaultContext(image.cols, image.rows);
+    mpe_params p; std::memset(&p, 0, sizeof(p));
+    p.threshold_value = threshold_value; p.gaussian_sigma = gaussian_sigma; p.min_blob_area = min_blob_area; p.max_blob_area = max_blob_area;
+    p.max_width_height_distortion = max_width_height_distortion; p.max_circular_distortion = max_circular_distortion;
+    p.back_projection_pixel_tolerance = 3; p.nearest_neighbour_pixel_tolerance = 5; p.certainty_threshold = 0.75; p.valid_correspondence_threshold = 0.7;
+    detail::check(ctx, mpe_set_params(ctx, &p), "mpe_set_params");
+    double K[9]; detail::camera_to_rowmajor(camera_matrix_K, K);
+    detail::check(ctx, mpe_set_camera(ctx, K, camera_distortion_coeffs.data(), (int)camera_distortion_coeffs.size()), "mpe_set_camera");
+    findLedsWith(ctx, image, ROI, pixel_positions, distorted_detection_centers);
+  }
+
+  static void findLedsWith(mpe_ctx* ctx, const ImageT& image, RectT ROI, List2DPoints& pixel_positions, std::vector<Point2fT>& centers) {
+    double px[2 * MPE_MAX_BLOBS]; float ce[2 * MPE_MAX_BLOBS]; int n = 0, flags = 0;
+    mpe_rect r; r.x = ROI.x; r.y = ROI.y; r.width = ROI.width; r.height = ROI.height;
+    detail::check(ctx, mpe_find_leds(ctx, image.data, (int)(size_t)image.step, image.cols, image.rows, r, px, ce, &n, &flags), "mpe_find_leds");
+    centers.clear();
+    for (int i = 0; i < n; ++i) centers.push_back(Point2fT(ce[2 * i], ce[2 * i + 1]));       // led_detector.cpp:89
+    if (n > 0) {                                                                               // :91 — untouched when nothing is found
+      pixel_positions.resize(n);
+      for (int i = 0; i < n; ++i) { pixel_positions(i)(0) = px[2 * i]; pixel_positions(i)(1) = px[2 * i + 1]; }
+    }
+  }
+
+  // led_detector.cpp:181-224
+  static void distortPoints(const std::vector<Point2fT>& src, std::vector<Point2fT>& dst, const CameraMatT& K, const std::vector<double>& D) {
+    dst.clear();
+    const double fx = cam_at(K, 0, 0), fy = cam_at(K, 1, 1), cx = cam_at(K, 0, 2), cy = cam_at(K, 1, 2);
+    const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
+    for (size_t i = 0; i < src.size(); ++i) {
+      const double x = ((double)src[i].x - cx) / fx, y = ((double)src[i].y - cy) / fy;
+      const double r2 = x * x + y * y;
+      double xc = x * (1. + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2), yc = y * (1. + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2);
+      xc = xc + (2. * p1 * x * y + p2 * (r2 + 2. * x * x));
+      yc = yc + (p1 * (r2 + 2. * y * y) + 2. * p2 * x * y);
+      dst.push_back(Point2fT((float)(xc * fx + cx), (float)(yc * fy + cy)));
+    }
+  }
+
+  // led_detector.cpp:114-179
+  static RectT determineROI(List2DPoints pixel_positions, SizeT image_size, const int border_size, const CameraMatT& K, const std::vector<double>& D) {
+    double x_min = INFINITY, x_max = 0, y_min = INFINITY, y_max = 0;
+    for (unsigned i = 0; i < pixel_positions.size(); ++i) {
+      if (pixel_positions(i)(0) < x_min) x_min = pixel_positions(i)(0);
+      if (pixel_positions(i)(0) > x_max) x_max = pixel_positions(i)(0);
+      if (pixel_positions(i)(1) < y_min) y_min = pixel_positions(i)(1);
+      if (pixel_positions(i)(1) > y_max) y_max = pixel_positions(i)(1);
+    }
+    std::vector<Point2fT> und, dis;
+    und.push_back(Point2fT((float)x_min, (float)y_min));
+    und.push_back(Point2fT((float)x_max, (float)y_max));
+    distortPoints(und, dis, K, D);
+    const double x0 = std::max(0.0, std::min((double)image_size.width, (double)dis[0].x - border_size));
+    const double x1 = std::max(0.0, std::min((double)image_size.width, (double)dis[1].x + border_size));
+    const double y0 = std::max(0.0, std::min((double)image_size.height, (double)dis[0].y - border_size));
+    const double y1 = std::max(0.0, std::min((double)image_size.height, (double)dis[1].y + border_size));
+    if (x1 - x0 < 1 || y1 - y0 < 1) return RectT(0, 0, image_size.width, image_size.height);
+    return RectT((int)x0, (int)y0, (int)(x1 - x0), (int)(y1 - y0));
+  }
+
+ private:
+  static mpe_ctx* defaultContext(int w, int h) {
+    static mpe_ctx* ctx = nullptr; static int cw = 0, ch = 0;
+    if (!ctx || w > cw || h > ch) {
+      if (ctx) mpe_destroy(ctx);
+      cw = w > cw ? w : cw; ch = h > ch ? h : ch;
+      if (mpe_create(&ctx, 0, 1, cw, ch) != MPE_OK) { ctx = nullptr; throw std::runtime_error("mpe_create failed: no CUDA device? (there is no CPU fallback)"); }
+    }
+    return ctx;
+  }
+};
+
+class PoseEstimator {
+ public:
+  // public tunables, written directly by the caller (pose_estimator.h:82-91)
+  CameraMatT camera_matrix_K_;
+  std::vector<double> camera_distortion_coeffs_;
+  int detection_threshold_value_;
+  double gaussian_sigma_, min_blob_area_, max_blob_area_, max_width_height_distortion_, max_circular_distortion_;
+  unsigned roi_border_thickness_;
+
+  PoseEstimator() : ctx_(nullptr), ctx_w_(0), ctx_h_(0) {                      // pose_estimator.cpp:34-42
+    back_projection_pixel_tolerance_ = 3; nearest_neighbour_pixel_tolerance_ = 5; certainty_threshold_ = 0.75;
+    valid_correspondence_threshold_ = 0.7; it_since_initialized_ = 0; histogram_threshold_ = 0; pose_updated_ = false;
+    detection_threshold_value_ = 0; gaussian_sigma_ = 0.6; min_blob_area_ = 0; max_blob_area_ = 0; max_width_height_distortion_ = 0;
+    max_circular_distortion_ = 0; roi_border_thickness_ = 0; current_time_ = previous_time_ = predicted_time_ = 0;
+    identity(current_pose_); identity(previous_pose_); identity(predicted_pose_);
+    for (int i = 0; i < 36; ++i) cov_[i] = 0;
+  }
+  ~PoseEstimator() { if (ctx_) mpe_destroy(ctx_); }
+  PoseEstimator(const PoseEstimator&) = delete;
+  PoseEstimator& operator=(const PoseEstimator&) = delete;
+
+  void setMarkerPositions(List4DPoints positions) {                             // :50-55
+    object_points_ = positions;
+    predicted_pixel_positions_.resize(object_points_.size());
+    unsigned n = (unsigned)object_points_.size();
+    histogram_threshold_ = numCombinations(n, 3);
+    markers_dirty_ = true;
+  }
+  List4DPoints getMarkerPositions() { return object_points_; }
+  void setPredictedPose(const Matrix4dT& pose, double time) { fromEigen(pose, predicted_pose_); predicted_time_ = time; }
+  Matrix4dT getPredictedPose() { return toEigen(predicted_pose_); }
+  Matrix6d getPoseCovariance() { Matrix6d c; for (int r = 0; r < 6; ++r) for (int q = 0; q < 6; ++q) c(r, q) = cov_[6 * r + q]; return c; }
+  void setImagePoints(List2DPoints points) { image_points_ = points; }
+  List2DPoints getImagePoints() { return image_points_; }
+  void setPredictedPixels(List2DPoints points) { predicted_pixel_positions_ = points; }
+  List2DPoints getPredictedPixelPositions() { return predicted_pixel_positions_; }
+  void setCorrespondences(VectorXuPairs corrs) { correspondences_ = corrs; }
+  VectorXuPairs getCorrespondences() { return correspondences_; }
+  void setBackProjectionPixelTolerance(double t) { back_projection_pixel_tolerance_ = t; }
+  double getBackProjectionPixelTolerance() { return back_projection_pixel_tolerance_; }
+  void setNearestNeighbourPixelTolerance(double t) { nearest_neighbour_pixel_tolerance_ = t; }
+  double getNearestNeighbourPixelTolerance() { return nearest_neighbour_pixel_tolerance_; }
+  void setCertaintyThreshold(double t) { certainty_threshold_ = t; }
+  double getCertaintyThreshold() { return certainty_threshold_; }
+  void setValidCorrespondenceThreshold(double t) { valid_correspondence_threshold_ = t; }
+  double getValidCorrespondenceThreshold() { return valid_correspondence_threshold_; }
+  void setHistogramThreshold(unsigned t) { histogram_threshold_ = t; }
+  unsigned getHistogramThreshold() { return histogram_threshold_; }
+  void setPredictedTime(double t) { predicted_time_ = t; }
+  double getPredictedTime() { return predicted_time_; }
+  unsigned lastGaussNewtonIterations() const { return last_gn_iters_; }
+
+  // pose_estimator.cpp:62-147
+  bool estimateBodyPose(ImageT image, double time_to_predict) {
+    pose_updated_ = false;
+    ensureContext(image.cols, image.rows);
+    List2DPoints detected;
+    if (it_since_initialized_ < 1) {
+      setPredictedTime(time_to_predict);
+      region_of_interest_ = RectT(0, 0, image.cols, image.rows);
+      LEDDetector::findLedsWith(ctx_, image, region_of_interest_, detected, distorted_detection_centers_);
+      if (detected.size() >= min_num_leds_detected_) {
+        setImagePoints(detected);
+        if (initialise() == 1) optimiseAndUpdatePose(time_to_predict);
+      }
+    } else {
+      predictWithROI(time_to_predict, image);
+      LEDDetector::findLedsWith(ctx_, image, region_of_interest_, detected, distorted_detection_centers_);
+      bool repeat_check = true; unsigned num_loops = 0;
+      do {
+        num_loops++;
+        if (detected.size() >= min_num_leds_detected_) {
+          setImagePoints(detected);
+          findCorrespondencesAndPredictPose(time_to_predict);
+          repeat_check = false;
+        } else if (num_loops < 2) {
+          region_of_interest_ = RectT(0, 0, image.cols, image.rows);
+          LEDDetector::findLedsWith(ctx_, image, region_of_interest_, detected, distorted_detection_centers_);
+        } else {
+          repeat_check = false;
+        }
+      } while (repeat_check);
+    }
+    return pose_updated_;
+  }
+
+  unsigned initialise() {                                                       // :544-721 (K2 + K3a + Kabsch)
+    push();
+    std::vector<double> det; flatten(image_points_, det);
+    uint32_t corr[2 * MPE_MAX_LEDS]; int k = 0, ok = 0; double pose[16];
+    detail::check(ctx_, mpe_initialise(ctx_, det.data(), (int)image_points_.size(), nullptr, corr, &k, pose, &ok), "mpe_initialise");
+    correspondences_.resize(k, 2);
+    for (int i = 0; i < k; ++i) { correspondences_(i, 0) = corr[2 * i]; correspondences_(i, 1) = corr[2 * i + 1]; }
+    if (ok) std::memcpy(predicted_pose_, pose, sizeof(pose));
+    return (unsigned)ok;
+  }
+  unsigned checkCorrespondences() {                                             // :394-542
+    push();
+    if (correspondences_.rows() < 4) return 0;
+    std::vector<double> det; flatten(image_points_, det);
+    std::vector<uint32_t> corr; flattenCorr(corr);
+    int ok = 0; double pose[16];
+    detail::check(ctx_, mpe_check_correspondences(ctx_, det.data(), (int)image_points_.size(), corr.data(), correspondences_.rows(), pose, &ok), "mpe_check_correspondences");
+    if (ok) std::memcpy(predicted_pose_, pose, sizeof(pose));
+    return (unsigned)ok;
+  }
+  void optimisePose() {                                                         // :733-792
+    push();
+    std::vector<double> det; flatten(image_points_, det);
+    std::vector<uint32_t> corr; flattenCorr(corr);
+    int it = 0;
+    detail::check(ctx_, mpe_optimise_pose(ctx_, det.data(), (int)image_points_.size(), corr.data(), correspondences_.rows(), predicted_pose_, cov_, &it), "mpe_optimise_pose");
+    last_gn_iters_ = (unsigned)it;
+  }
+  void updatePose() {                                                           // :794-800
+    std::memcpy(previous_pose_, current_pose_, sizeof(current_pose_)); std::memcpy(current_pose_, predicted_pose_, sizeof(current_pose_));
+    previous_time_ = current_time_; current_time_ = predicted_time_;
+  }
+  void optimiseAndUpdatePose(double&) {                                         // :802-812
+    optimisePose();
+    if (it_since_initialized_ < 2) it_since_initialized_++;
+    updatePose();
+    pose_updated_ = true;
+  }
+  void predictWithROI(double& time_to_predict, const ImageT& image) {           // :814-829
+    if (it_since_initialized_ >= 2) predictPose(time_to_predict); else setPredictedTime(time_to_predict);
+    predictMarkerPositionsInImage();
+    region_of_interest_ = LEDDetector::determineROI(getPredictedPixelPositions(), SizeT(image.cols, image.rows), (int)roi_border_thickness_,
+                                                   camera_matrix_K_, camera_distortion_coeffs_);
+  }
+  void findCorrespondencesAndPredictPose(double& time_to_predict) {             // :831-848
+    findCorrespondences();
+    if (checkCorrespondences() == 1) optimiseAndUpdatePose(time_to_predict);
+    else if (initialise() == 1) optimiseAndUpdatePose(time_to_predict);
+  }
+  void predictMarkerPositionsInImage() {                                        // :270-276 with project2d :251-268
+    predicted_pixel_positions_.resize(object_points_.size());
+    double K[9]; detail::camera_to_rowmajor(camera_matrix_K_, K);
+    for (unsigned i = 0; i < object_points_.size(); ++i) {
+      double p[4] = {object_points_(i)(0), object_points_(i)(1), object_points_(i)(2), object_points_(i)(3)}, c[3], t[3];
+      for (int r = 0; r < 3; ++r) c[r] = predicted_pose_[4 * r] * p[0] + predicted_pose_[4 * r + 1] * p[1] + predicted_pose_[4 * r + 2] * p[2] + predicted_pose_[4 * r + 3] * p[3];
+      for (int r = 0; r < 3; ++r) t[r] = K[3 * r] * c[0] + K[3 * r + 1] * c[1] + K[3 * r + 2] * c[2];
+      predicted_pixel_positions_(i)(0) = t[0] / t[2]; predicted_pixel_positions_(i)(1) = t[1] / t[2];
+    }
+  }
+  void findCorrespondences() {                                                  // :372-392 (+ :862-906)
+    std::vector<unsigned> rows;
+    for (unsigned i = 0; i < predicted_pixel_positions_.size(); ++i) {
+      double best = INFINITY; unsigned bj = 0;
+      for (unsigned j = 0; j < image_points_.size(); ++j) {
+        const double dx = predicted_pixel_positions_(i)(0) - image_points_(j)(0), dy = predicted_pixel_positions_(i)(1) - image_points_(j)(1);
+        const double d2 = dx * dx + dy * dy;
+        if (d2 < best) { best = d2; bj = j + 1; }
+      }
+      if (std::sqrt(best) <= nearest_neighbour_pixel_tolerance_) { rows.push_back(i + 1); rows.push_back(bj); }
+    }
+    correspondences_.resize((int)rows.size() / 2, 2);
+    for (size_t i = 0; i < rows.size() / 2; ++i) { correspondences_((int)i, 0) = rows[2 * i]; correspondences_((int)i, 1) = rows[2 * i + 1]; }
+  }
+  void predictPose(double time_to_predict) {                                    // :232-244
+    predicted_time_ = time_to_predict;
+    double inv[16], rel[16], delta[6], delta_hat[6], E[16], out[16];
+    detail::rigid_inverse(previous_pose_, inv);
+    detail::mul44(inv, current_pose_, rel);
+    logarithmMap(rel, delta);
+    for (int i = 0; i < 6; ++i) delta_hat[i] = delta[i] / (current_time_ - previous_time_) * (predicted_time_ - current_time_);
+    exponentialMap(delta_hat, E);
+    detail::mul44(current_pose_, E, out);
+    std::memcpy(predicted_pose_, out, sizeof(out));
+  }
+
+  static void exponentialMap(const double twist[6], double T[16]) {             // :962-994
+    const double wx = twist[3], wy = twist[4], wz = twist[5];
+    const double th = std::sqrt(wx * wx + wy * wy + wz * wz), th2 = th * th;
+    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double O2[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+    double R[9], V[9];
+    for (int i = 0; i < 9; ++i) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      if (th == 0) { R[i] = I; V[i] = I; }
+      else { R[i] = I + O[i] / th * std::sin(th) + O2[i] / th2 * (1 - std::cos(th)); V[i] = I + (1 - std::cos(th)) / th2 * O[i] + (th - std::sin(th)) / (th2 * th) * O2[i]; }
+    }
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c]; T[4 * r + 3] = V[3 * r] * twist[0] + V[3 * r + 1] * twist[1] + V[3 * r + 2] * twist[2]; }
+    T[12] = T[13] = T[14] = 0; T[15] = 1;
+  }
+  static void logarithmMap(const double T[16], double xi[6]) {                  // :996-1064
+    double R[9], t[3]; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[3 * r + c] = T[4 * r + c]; t[r] = T[4 * r + 3]; }
+    double w_hat[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double dn = 0, rn = 0; for (int i = 0; i < 9; ++i) { const double I = (i % 4 == 0) ? 1.0 : 0.0; dn += (R[i] - I) * (R[i] - I); rn += R[i] * R[i]; }
+    if (!(dn <= 1e-20 * std::min(rn, 3.0))) {
+      double temp = (R[0] + R[4] + R[8] - 1) / 2; if (temp > 1) temp = 1; else if (temp < -1) temp = -1;
+      const double phi = std::acos(temp);
+      if (phi != 0) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) w_hat[3 * r + c] = (R[3 * r + c] - R[3 * c + r]) / (2 * std::sin(phi)) * phi;
+    }
+    const double w[3] = {w_hat[7], w_hat[2], w_hat[3]};
+    const double wn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double A[9];
+    if (t[0] == 0 && t[1] == 0 && t[2] == 0) { for (int i = 0; i < 9; ++i) A[i] = 0; }
+    else if (wn == 0 || std::sin(wn) == 0) { for (int i = 0; i < 9; ++i) A[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    else {
+      const double k = (2 * std::sin(wn) - wn * (1 + std::cos(wn))) / (2 * wn * wn * std::sin(wn));
+      double w2[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w2[3 * i + j] = w_hat[3 * i] * w_hat[j] + w_hat[3 * i + 1] * w_hat[3 + j] + w_hat[3 * i + 2] * w_hat[6 + j];
+      for (int i = 0; i < 9; ++i) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - w_hat[i] / 2 + k * w2[i];
+    }
+    for (int r = 0; r < 3; ++r) xi[r] = A[3 * r] * t[0] + A[3 * r + 1] * t[1] + A[3 * r + 2] * t[2];
+    xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];
+  }
+
+  const RectT& regionOfInterest() const { return region_of_interest_; }
+  const double* predictedPoseRowMajor() const { return predicted_pose_; }
+
+ private:
+  static const unsigned min_num_leds_detected_ = 4;                             // pose_estimator.h:78
+  static unsigned factorial(int N) { return (N == 1 || N == 0) ? 1u : factorial(N - 1) * (unsigned)N; }          // combinations.cpp:34-40
+  static unsigned numCombinations(unsigned N, unsigned K) { return (N >= K) ? factorial((int)N) / (factorial((int)K) * factorial((int)(N - K))) : 0u; }
+  static void identity(double* T) { for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+  static Matrix4dT toEigen(const double* T) { Matrix4dT m; for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) m(r, c) = T[4 * r + c]; return m; }
+  static void fromEigen(const Matrix4dT& m, double* T) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[4 * r + c] = m(r, c); }
+  static void flatten(const List2DPoints& l, std::vector<double>& out) { out.resize(2 * l.size()); for (unsigned i = 0; i < l.size(); ++i) { out[2 * i] = l(i)(0); out[2 * i + 1] = l(i)(1); } }
+  void flattenCorr(std::vector<uint32_t>& out) const { out.resize(2 * (size_t)correspondences_.rows()); for (int i = 0; i < correspondences_.rows(); ++i) { out[2 * i] = correspondences_(i, 0); out[2 * i + 1] = correspondences_(i, 1); } }
+
+  void ensureContext(int w, int h) {
+    if (ctx_ && w <= ctx_w_ && h <= ctx_h_) return;
+    if (ctx_) mpe_destroy(ctx_);
+    ctx_ = nullptr; ctx_w_ = w; ctx_h_ = h;
+    if (mpe_create(&ctx_, 0, 1, w, h) != MPE_OK) { ctx_ = nullptr; throw std::runtime_error("mpe_create failed: no CUDA device? (there is no CPU fallback)"); }
+    markers_dirty_ = true;
+  }
+  void push() {   // the caller writes the public fields directly, so configuration is pushed before every device stage
+    if (!ctx_) ensureContext(752, 480);
+    mpe_params p; std::memset(&p, 0, sizeof(p));
+    p.threshold_value = detection_threshold_value_; p.roi_border_thickness = (int)roi_border_thickness_; p.gaussian_sigma = gaussian_sigma_;
+    p.min_blob_area = min_blob_area_; p.max_blob_area = max_blob_area_; p.max_width_height_distortion = max_width_height_distortion_;
+    p.max_circular_distortion = max_circular_distortion_; p.back_projection_pixel_tolerance = back_projection_pixel_tolerance_;
+    p.nearest_neighbour_pixel_tolerance = nearest_neighbour_pixel_tolerance_; p.certainty_threshold = certainty_threshold_;
+    p.valid_correspondence_threshold = valid_correspondence_threshold_;
+    detail::check(ctx_, mpe_set_params(ctx_, &p), "mpe_set_params");
+    double K[9]; detail::camera_to_rowmajor(camera_matrix_K_, K);
+    detail::check(ctx_, mpe_set_camera(ctx_, K, camera_distortion_coeffs_.data(), (int)camera_distortion_coeffs_.size()), "mpe_set_camera");
+    if (markers_dirty_) {
+      std::vector<double> xyz(3 * object_points_.size());
+      for (unsigned i = 0; i < object_points_.size(); ++i) for (int k = 0; k < 3; ++k) xyz[3 * i + k] = object_points_(i)(k);
+      detail::check(ctx_, mpe_set_markers(ctx_, xyz.data(), (int)object_points_.size()), "mpe_set_markers");
+      markers_dirty_ = false;
+    }
+    detail::check(ctx_, mpe_set_histogram_threshold(ctx_, histogram_threshold_), "mpe_set_histogram_threshold");
+  }
+
+  mpe_ctx* ctx_; int ctx_w_, ctx_h_; bool markers_dirty_ = true;
+  double current_pose_[16], previous_pose_[16], predicted_pose_[16], cov_[36];   // row-major
+  double current_time_, previous_time_, predicted_time_;
+  List4DPoints object_points_;
+  List2DPoints image_points_, predicted_pixel_positions_;
+  VectorXuPairs correspondences_;
+  double back_projection_pixel_tolerance_, nearest_neighbour_pixel_tolerance_, certainty_threshold_, valid_correspondence_threshold_;
+  unsigned histogram_threshold_, it_since_initialized_, last_gn_iters_ = 0;
+  std::vector<Point2fT> distorted_detection_centers_;
+  RectT region_of_interest_;
+  bool pose_updated_;
+};
+
+}  // namespace monocular_pose_estimator
+#endif  // MPE_B200_SHIM_H_

@@ -1,0 +1,49 @@
+"""The C++ class shim (include/monocular_pose_estimator_b200/shim.h) driven like MPENode drives the reference library must
+reproduce the oracle's estimateBodyPose sequence (cold start + ROI tracking)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from rpg_monocular_pose_estimator_b200 import synth
+from oracle import pose_oracle
+from tests.helpers import pose_error
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_shim_tracking_sequence(tmp_path):
+    exe = os.path.join(ROOT, "build", "shim_demo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["python", "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
+    sc = synth.make_stream_scene(20, n_leds=5, seed=21)
+    p = sc.params
+    scene = tmp_path / "scene.bin"
+    with open(scene, "wb") as f:
+        f.write(struct.pack("4i", len(sc.frames), sc.width, sc.height, len(sc.markers)))
+        f.write(np.ascontiguousarray(sc.K, np.float64).tobytes()); f.write(np.ascontiguousarray(sc.D[:5], np.float64).tobytes())
+        f.write(np.ascontiguousarray(sc.markers, np.float64).tobytes())
+        f.write(np.array([p.threshold_value, p.gaussian_sigma, p.min_blob_area, p.max_blob_area, p.max_width_height_distortion,
+                          p.max_circular_distortion, p.back_projection_pixel_tolerance, p.nearest_neighbour_pixel_tolerance,
+                          p.certainty_threshold, p.valid_correspondence_threshold, p.roi_border_thickness], np.float64).tobytes())
+        f.write(np.ascontiguousarray(sc.times, np.float64).tobytes()); f.write(sc.frames.tobytes())
+    out = subprocess.run([exe, str(scene)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(lines) == len(sc.frames)
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    n_ok = 0
+    for fi, l in enumerate(lines):
+        upd = est.estimate_body_pose(sc.frames[fi], sc.times[fi])
+        assert int(l[1]) == int(upd), fi
+        assert tuple(int(v) for v in l[2:6]) == tuple(est.region_of_interest), fi
+        if upd:
+            n_ok += 1
+            T = np.array([float(v) for v in l[7:23]]).reshape(4, 4)
+            dt, dr = pose_error(T, est.predicted_pose())
+            assert dt < 1e-6 and dr < 1e-6, (fi, dt, dr)
+            assert int(l[6]) == est.gn_iterations()
+    assert n_ok >= 18
