@@ -44,7 +44,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -59,7 +59,10 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarises the samples taken between two wall-clock times (time.time()); nvidia-smi is started long before the
+        timed region because its first sample takes about a second."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -75,13 +78,17 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and (ts < t_begin - 0.02 or ts > t_end + 0.02):
+                    continue
+                sm_v, mx_v = float(parts[2]), float(parts[3])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[5:9]):
+            sm.append(sm_v); mx.append(mx_v)
+            for n, v in zip(names, parts[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
@@ -107,13 +114,30 @@ def _cpu_worker_init(K, D, markers, params):
     _W = dict(K=K, D=D, markers=markers, params=params, po=pose_oracle)
 
 
-def _cpu_worker_run(frames):
+_FRAMES = None   # set in the parent before the fork so that workers get the frames without any IPC
+
+
+def _cpu_worker_run(idx):
     po = _W["po"]
     n_upd = 0
-    for fr in frames:
+    for i in idx:
+        fr = _FRAMES[i % len(_FRAMES)]
         est = po.PoseEstimatorOracle(_W["K"], _W["D"], _W["markers"], _W["params"])
         n_upd += int(est.estimate_body_pose(fr, 0.0))
     return n_upd
+
+
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128
+    logical CPUs but grant a 16-CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 def cpu_single_thread(scene, max_seconds=15.0, max_frames=4000):
@@ -141,12 +165,13 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     from rpg_monocular_pose_estimator_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_core = 48
     sample = cores * per_core
     scene = synth.make_cold_scene(min(sample, 512), n_leds=N_LEDS, width=WIDTH, height=HEIGHT, seed=args.seed)
-    frames = [scene.frames[i % len(scene.frames)] for i in range(sample)]
-    chunks = [frames[i::cores] for i in range(cores)]
+    global _FRAMES
+    _FRAMES = scene.frames
+    chunks = [list(range(i, sample, cores)) for i in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(scene.K, scene.D, scene.markers, scene.params)) as pool:
         for _ in range(max(args.warmup, 1)):
@@ -207,6 +232,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # started early: nvidia-smi needs ~1 s before its first sample
     W, H, B = args.width, args.height, args.batch
     scene = synth.make_cold_scene(B, n_leds=args.leds, width=W, height=H, seed=args.seed + 100000 * rank)
     host_frames = torch.from_numpy(scene.frames).pin_memory()          # B x H x W u8, pinned
@@ -247,8 +274,7 @@ def main():
             if upd:
                 assert np.abs(res[f]["pose"].reshape(4, 4) - est.predicted_pose()).max() < 1e-6, "GPU/oracle pose mismatch"
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()                      # sampled from the warm-up on: the timed region alone can be shorter than one sample period
+    t_load0 = time.time()                # clocks are summarised over warm-up + timed steps (both under the same load)
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -262,7 +288,8 @@ def main():
     ms_total = e0.elapsed_time(e1)
     launches_timed = ctx.launch_count() - launches1
     kt = ctx.kernel_times_ms()                      # last step's per-kernel CUDA-event durations
-    clocks = sampler.stop()
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -333,7 +360,7 @@ def main():
             fps, n, dt = cpu_single_thread(scene)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
                                     "sample": f"{n} frames of the same batch in {dt:.1f} s, one thread (cv2 4.13 findLeds + C++ oracle of the pose path)",
-                                    "host_cpus": os.cpu_count()}
+                                    "host_cpus": os.cpu_count(), "host_cpus_usable": usable_cores()}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

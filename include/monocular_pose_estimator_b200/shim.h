@@ -252,6 +252,7 @@ class PoseEstimator {
   bool estimateBodyPose(ImageT image, double time_to_predict) {
     pose_updated_ = false;
     ensureContext(image.cols, image.rows);
+    push();   // the caller may have changed the public fields since the last frame
     List2DPoints detected;
     if (it_since_initialized_ < 1) {
       setPredictedTime(time_to_predict);
