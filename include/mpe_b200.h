@@ -170,8 +170,13 @@ int mpe_copy_poses_device(mpe_ctx* ctx, int n_frames, double* poses_device);
  * (current/previous/predicted pose, times, it_since_initialized_).  One call advances every stream by
  * one frame exactly as estimateBodyPose does (predictWithROI, ROI findLeds, findCorrespondences,
  * checkCorrespondences, fall back to initialise, whole-image retry; pose_estimator.cpp:97-144).
- * frames_device: one frame per stream. */
+ * frames_device: one frame per stream; times: HOST array of n_streams time stamps; results: HOST array or NULL (then
+ * fetch them later with mpe_fetch_results). */
 int mpe_streams_reset(mpe_ctx* ctx, int n_streams);
+/* Optional indirection for the next mpe_streams_step_device calls: stream s reads image frame_index_device[s] of the buffer
+ * (a DEVICE array of n_streams ints; NULL = stream s reads image s).  n_frames_in_buffer = images addressable from the
+ * frames pointer.  Lets many streams replay a smaller set of recorded sequences. */
+int mpe_streams_set_frame_map(mpe_ctx* ctx, const int* frame_index_device, int n_frames_in_buffer);
 int mpe_streams_step_device(mpe_ctx* ctx, const uint8_t* frames_device, int pitch, long long frame_stride,
                             int width, int height, int n_streams, const double* times, mpe_result* results);
 

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_consta
       int x_elem0 = tile_elem0(c.roi.x + c.ct * g.tw_px - R);
       int y0 = c.roi.y + c.s * kTileRows - R;
       mbar_expect_tx(&bars[stage], stage_bytes);
-      tma_load_3d(ring + (size_t)stage * stage_stride, &tmap, &bars[stage], x_elem0, y0, c.f);
+      tma_load_3d(ring + (size_t)stage * stage_stride, &tmap, &bars[stage], x_elem0, y0, g.frame_map ? g.frame_map[c.f] : c.f);
       return;
     }
   };
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
     const int out_rows = min(kTileRows, c.roi.h - c.s * kTileRows);
     const int tile_x0 = c.roi.x + c.ct * g.tw_px;                      // output pixel range of this tile
     const int tile_x1 = min(c.roi.x + c.roi.w, tile_x0 + g.tw_px);
-    const uint8_t* frame = a.frames + (size_t)c.f * a.frame_stride;
+    const uint8_t* frame = a.frames + (size_t)(g.frame_map ? g.frame_map[c.f] : c.f) * a.frame_stride;
 
     // (B) every hot source word marks the output words it can influence: rows row-2R..row, words j-1..j+1
     if (rec.y == 0xffffffffu) {                      // dense hand-over: every word of the tile is a candidate
@@ -762,6 +762,7 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kBlobWarpsPerCta + warp;
   if (f >= a.g.n_frames) return;
+  if (a.active && !a.active[f]) return;
   WarpScratch& ws = scratch[warp];
   const K1Geom& g = a.g;
   const Roi roi = g.rois ? g.rois[f] : g.roi;

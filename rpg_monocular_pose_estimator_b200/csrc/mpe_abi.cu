@@ -18,6 +18,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+constexpr int kTrackTileWidthPx = 256;   // column-tile width of the tracking-mode K1 launches (ROIs are ~100-200 px wide)
 constexpr size_t kPoolPerFrame = 1024;   // hot-word pool entries reserved per frame of capacity (overflow degrades to the dense path)
 
 struct DevBuffers {
@@ -43,6 +44,13 @@ struct DevBuffers {
   uint4* hot_tiles = nullptr;      // [max_batch * flags_per_frame]
   uint16_t* pool = nullptr;        // [max_batch * kPoolPerFrame]
   uint32_t* counters = nullptr;    // [2]
+  // tracking loop
+  StreamState* streams = nullptr;  // [max_batch]
+  Roi* result_rois = nullptr;      // [max_batch]
+  double* pred_px = nullptr;       // [max_batch][MPE_MAX_LEDS][2]
+  uint8_t* masks = nullptr;        // 6 x [max_batch]: mode, done, a_retry, a_check, a_init, a_gn
+  int* track_flags = nullptr;      // [max_batch]
+  double* times = nullptr;         // [max_batch]
   int* check_cnt = nullptr;        // [max_batch][2]
 };
 
@@ -69,6 +77,8 @@ struct mpe_ctx {
   long long launches = 0;
   std::string err;
   PFN_encodeTiled encode = nullptr;
+  const int* frame_map = nullptr;   // optional stream -> image index table for mpe_streams_step_device
+  int frame_map_total = 0;
   std::vector<cudaEvent_t> chunk_events;
 };
 
@@ -140,16 +150,18 @@ struct FrameSource {
   int n_frames_total;       // frames addressable from base
 };
 
-int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_h, int radius, K1Geom* g) {
+int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_h, int radius, int forced_tw, K1Geom* g) {
   g->img_w = w; g->img_h = h;
   g->roi = roi; g->rois = nullptr;
   g->max_roi_w = max_roi_w; g->max_roi_h = max_roi_h;
   g->n_strips = (max_roi_h + kTileRows - 1) / kTileRows;
   int tw = max_roi_w;
   if (tw > kMaxTileWidthPx) tw = kMaxTileWidthPx;          // 960 = 30 mask words
+  if (forced_tw > 0 && forced_tw < tw) tw = forced_tw;     // tracking: narrow column tiles (multiple of 32) for small ROIs
   g->n_ct = (max_roi_w + tw - 1) / tw;
-  if (g->n_ct > 1) tw = kMaxTileWidthPx;
+  if (g->n_ct > 1 && forced_tw <= 0) tw = kMaxTileWidthPx;
   g->tw_px = tw;
+  g->frame_map = nullptr;
   // widest span of u32 elements a tile can touch: it starts at the 16-pixel boundary at or below x - R (TMA needs a
   // 16-byte aligned innermost coordinate) and must reach pixel x + tw + R - 1
   int span = (tw + 2 * radius - 1 + 15) / 4 + 1;
@@ -187,20 +199,22 @@ void time_begin(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) cudaEventRe
 void time_end(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) { cudaEventRecord(c->ev[2 * k + 1], st); c->timing_pending = true; } }
 
 // K1a + K1b over frames [f0, f0+n) of `src`, outputs into slots [slot0, slot0+n) of the context buffers.
-int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, Roi roi, const Roi* rois_dev, cudaStream_t st) {
+int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, Roi roi, const Roi* rois_dev, cudaStream_t st,
+                  int forced_tw = 0, const int* frame_map = nullptr, const uint8_t* active = nullptr) {
   int radius = 0;
   K1aArgs a{};
   if (!gaussian_taps_8u(c->params.gaussian_sigma, &radius, a.taps))
     return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "]");
   int max_w = rois_dev ? src.width : roi.w, max_h = rois_dev ? src.height : roi.h;
-  int rc = make_geometry(c, src.width, src.height, roi, max_w, max_h, radius, &a.g);
+  int rc = make_geometry(c, src.width, src.height, roi, max_w, max_h, radius, forced_tw, &a.g);
   if (rc != MPE_OK) return fail(c, rc, "ROI / image too large for this context");
   a.g.n_frames = n;
   a.g.rois = rois_dev;
+  a.g.frame_map = frame_map;
   CUtensorMap tmap;
   FrameSource sub = src;
   sub.base = src.base + (size_t)f0 * src.frame_stride;
-  sub.n_frames_total = n;
+  sub.n_frames_total = frame_map ? src.n_frames_total : n;
   rc = encode_tensor_map(c, sub, a.g.box_w, kTileRows + 2 * radius, &tmap);
   if (rc != MPE_OK) return rc;
   int T = c->params.threshold_value;
@@ -240,6 +254,7 @@ int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, 
   b.flags = c->d.flags + slot0;
   b.det = c->d.det + (size_t)slot0 * MPE_MAX_BLOBS * 2;
   b.centers = c->d.centers + (size_t)slot0 * MPE_MAX_BLOBS * 2;
+  b.active = active;
   time_begin(c, 1, st);
   CUDA_TRY(c, launch_extract_blobs(b, st));
   time_end(c, 1, st);
@@ -392,8 +407,10 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   c->max_batch = max_batch; c->max_w = max_width; c->max_h = max_height;
   c->pitch = (max_width + 15) & ~15;
   int n_ct = (max_width + kMaxTileWidthPx - 1) / kMaxTileWidthPx;
+  int n_ct_track = (max_width + kTrackTileWidthPx - 1) / kTrackTileWidthPx;      // tracking mode uses narrow column tiles
   c->mask_wpr = (n_ct > 1) ? n_ct * (kMaxTileWidthPx / 32) : (max_width + 31) / 32;
-  c->flags_per_frame = ((max_height + kTileRows - 1) / kTileRows) * n_ct;
+  if (n_ct_track * (kTrackTileWidthPx / 32) > c->mask_wpr) c->mask_wpr = n_ct_track * (kTrackTileWidthPx / 32);
+  c->flags_per_frame = ((max_height + kTileRows - 1) / kTileRows) * (n_ct > n_ct_track ? n_ct : n_ct_track);
   CREATE_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CREATE_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -421,6 +438,13 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.hot_tiles, B * c->flags_per_frame));
   CREATE_TRY(dev_alloc(&c->d.pool, B * kPoolPerFrame));
   CREATE_TRY(dev_alloc(&c->d.counters, 2));
+  CREATE_TRY(dev_alloc(&c->d.streams, B));
+  CREATE_TRY(dev_alloc(&c->d.result_rois, B));
+  CREATE_TRY(dev_alloc(&c->d.pred_px, B * MPE_MAX_LEDS * 2));
+  CREATE_TRY(dev_alloc(&c->d.masks, 6 * B));
+  CREATE_TRY(dev_alloc(&c->d.track_flags, B));
+  CREATE_TRY(dev_alloc(&c->d.times, B));
+  CREATE_TRY(launch_track_reset(c->d.streams, max_batch, c->own_stream));
   CREATE_TRY(cudaMemset(c->d.n_corr, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.flags, 0, B * sizeof(int)));
   CREATE_TRY(cudaMemset(c->d.corr, 0, B * 2 * MPE_MAX_LEDS * sizeof(uint32_t)));
@@ -449,7 +473,8 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
   cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.done); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
-  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
+  cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
@@ -735,11 +760,68 @@ int mpe_copy_poses_device(mpe_ctx* c, int n_frames, double* poses_device) {
 }
 
 int mpe_streams_reset(mpe_ctx* c, int n_streams) {
-  (void)n_streams;
-  return fail(c, MPE_E_UNSUPPORTED, "device-side tracking loop not built yet");
+  if (!c || n_streams < 1 || n_streams > c->max_batch) return fail(c, MPE_E_INVALID, "n_streams must be in [1, max_batch]");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, launch_track_reset(c->d.streams, n_streams, c->stream));
+  ++c->launches;
+  return MPE_OK;
 }
-int mpe_streams_step_device(mpe_ctx* c, const uint8_t*, int, long long, int, int, int, const double*, mpe_result*) {
-  return fail(c, MPE_E_UNSUPPORTED, "device-side tracking loop not built yet");
+
+int mpe_streams_set_frame_map(mpe_ctx* c, const int* frame_index_device, int n_frames_in_buffer) {
+  if (!c) return MPE_E_INVALID;
+  c->frame_map = frame_index_device;
+  c->frame_map_total = n_frames_in_buffer;
+  return MPE_OK;
+}
+
+// One estimateBodyPose step for n_streams independent PoseEstimators (pose_estimator.cpp:62-147) without a host round trip.
+int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch, long long frame_stride, int width, int height,
+                            int n_streams, const double* times, mpe_result* results) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!frames_device || !times || n_streams < 1) return MPE_E_INVALID;
+  if (n_streams > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "streams or image larger than the context capacity");
+  if (c->cam.nD < 5) return fail(c, MPE_E_UNSUPPORTED, "LEDDetector::distortPoints reads five distortion coefficients (led_detector.cpp:190-194)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int n = n_streams;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  const size_t B = (size_t)c->max_batch;
+  TrackArgs t{};
+  t.n = n; t.img_w = width; t.img_h = height; t.roi_border = c->params.roi_border_thickness;
+  t.state = c->d.streams; t.times = c->d.times; t.cam = c->cam; t.pp = c->pp;
+  t.rois = c->d.rois; t.result_rois = c->d.result_rois; t.pred_px = c->d.pred_px;
+  t.mode = c->d.masks; t.done = c->d.masks + B; t.a_retry = c->d.masks + 2 * B; t.a_check = c->d.masks + 3 * B;
+  t.a_init = c->d.masks + 4 * B; t.a_gn = c->d.masks + 5 * B;
+  t.track_flags = c->d.track_flags;
+  t.n_det = c->d.n_det; t.flags = c->d.flags; t.det = c->d.det; t.centers = c->d.centers;
+  t.corr = c->d.corr; t.n_corr = c->d.n_corr; t.pose_io = c->d.pose; t.cov = c->d.cov; t.ok = c->d.ok; t.iters = c->d.iters; t.updated = c->d.updated;
+  const int total = c->frame_map ? c->frame_map_total : n;
+  FrameSource src{frames_device, pitch, frame_stride, width, height, total};
+  Roi full{0, 0, width, height};
+
+  CUDA_TRY(c, launch_track_begin(t, st));                                                        // predictWithROI
+  rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, nullptr);   // findLeds(ROI)
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, launch_track_after_detect(t, 0, st));
+  CUDA_TRY(c, launch_track_prepare_retry(t, st));
+  rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, t.a_retry);  // whole-image retry (only where needed)
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, launch_track_after_detect(t, 1, st));
+  rc = run_refine(c, 0, n, 1, st, t.a_check);                                                    // checkCorrespondences on the NN matches
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, launch_track_after_check(t, st));
+  rc = run_sweep(c, 0, n, st, t.a_init);                                                         // initialise(): cold streams + failed checks
+  if (rc != MPE_OK) return rc;
+  rc = run_refine(c, 0, n, 1, st, t.a_init);
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, launch_track_after_init(t, st));
+  rc = run_refine(c, 0, n, 2, st, t.a_gn);                                                       // optimisePose
+  if (rc != MPE_OK) return rc;
+  CUDA_TRY(c, launch_track_finish(t, c->d.results, st));
+  c->launches += 7;
+  if (results) return mpe_fetch_results(c, n, results);
+  return MPE_OK;
 }
 
 int mpe_enable_kernel_timing(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->timing = on != 0; return MPE_OK; }

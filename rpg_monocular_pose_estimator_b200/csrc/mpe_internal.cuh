@@ -51,6 +51,7 @@ struct K1Geom {
   int mask_wpr;              // u32 words per mask row
   int mask_rows;             // rows reserved per frame in the mask buffer
   int flags_per_frame;       // row-flag words reserved per frame
+  const int* frame_map;      // optional [n_frames]: index of the image (z coordinate / frame_stride multiple) each entry reads
 };
 
 struct K1aArgs {
@@ -81,6 +82,7 @@ struct K1bArgs {
   int* flags;                // [n_frames]
   double* det;               // [n_frames][MPE_MAX_BLOBS][2] undistorted
   float* centers;            // [n_frames][MPE_MAX_BLOBS][2] distorted
+  const uint8_t* active;     // optional [n_frames]: frames with 0 are left untouched
 };
 
 struct K2Args {
@@ -119,7 +121,39 @@ struct K3Args {
   int* check_cnt;            // [n_frames][2]  number of valid subsets, number of subsets
 };
 
+// Per-stream state of the tracking loop = the PoseEstimator members that survive a frame (pose_estimator.h:56-79)
+struct StreamState {
+  double current_pose[16], previous_pose[16], predicted_pose[16];   // row-major
+  double current_time, previous_time, predicted_time;
+  int it_since_initialized;
+  int pad;
+};
+
+struct TrackArgs {
+  int n;
+  int img_w, img_h, roi_border;
+  StreamState* state;
+  const double* times;       // [n] time_to_predict of this step
+  DevCamera cam;
+  DevPoseParams pp;
+  Roi* rois;                 // [n] ROI handed to K1 (empty = skip)
+  Roi* result_rois;          // [n] region_of_interest_ reported for the frame
+  double* pred_px;           // [n][MPE_MAX_LEDS][2] predicted_pixel_positions_
+  uint8_t *mode, *done, *a_retry, *a_check, *a_init, *a_gn;   // [n] each
+  int* track_flags;          // [n]
+  // buffers shared with the cold path
+  const int* n_det; const int* flags; const double* det; const float* centers;
+  uint32_t* corr; int* n_corr; double* pose_io; const double* cov; int* ok; int* iters; int* updated;
+};
+
 // ---- launchers (defined next to the kernels) ----
+cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st);
+cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st);
+cudaError_t launch_track_prepare_retry(const TrackArgs& a, cudaStream_t st);
+cudaError_t launch_track_after_check(const TrackArgs& a, cudaStream_t st);
+cudaError_t launch_track_after_init(const TrackArgs& a, cudaStream_t st);
+cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st);
+cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st);
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);

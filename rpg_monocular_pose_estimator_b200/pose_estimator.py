@@ -141,6 +141,22 @@ class Context:
         self.check(self.L.mpe_fetch_results(self.h, n, res))
         return res
 
+    # ---- device-resident tracking loop (one PoseEstimator per stream, state on the GPU)
+    def streams_reset(self, n_streams: int):
+        self.check(self.L.mpe_streams_reset(self.h, n_streams))
+
+    def streams_set_frame_map(self, frame_index_device_ptr: int, n_frames_in_buffer: int):
+        self.check(self.L.mpe_streams_set_frame_map(self.h, C.c_void_p(frame_index_device_ptr), n_frames_in_buffer))
+
+    def streams_step_device(self, dev_ptr: int, pitch: int, frame_stride: int, width: int, height: int, times, fetch: bool = True):
+        """One estimateBodyPose step for len(times) streams; frame s of the device buffer belongs to stream s (or
+        frame_map[s] when a frame map is set)."""
+        t = np.ascontiguousarray(times, np.float64)
+        n = len(t)
+        res = (MpeResult * n)() if fetch else None
+        self.check(self.L.mpe_streams_step_device(self.h, C.c_void_p(dev_ptr), pitch, frame_stride, width, height, n, _dp(t), res))
+        return res
+
     def copy_poses_device(self, dst_device_ptr: int, n: int):
         self.check(self.L.mpe_copy_poses_device(self.h, n, C.c_void_p(dst_device_ptr)))
 

@@ -1,0 +1,91 @@
+"""Device-resident tracking loop (mpe_streams_step_device): S independent streams advanced frame by frame on the GPU must
+reproduce, stream by stream and frame by frame, the oracle's estimateBodyPose (pose_estimator.cpp:62-147): update flag,
+region of interest, correspondences, Gauss-Newton iteration count, pose within 1e-6 m / 1e-6 rad."""
+import numpy as np
+import pytest
+
+from rpg_monocular_pose_estimator_b200 import synth
+from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+from oracle import pose_oracle
+from tests.helpers import pose_error
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(streams, ctx, torch):
+    S, T = len(streams), len(streams[0].frames)
+    sc0 = streams[0]
+    H, W = sc0.height, sc0.width
+    frames = np.stack([np.stack([streams[s].frames[t] for s in range(S)]) for t in range(T)])      # T x S x H x W
+    dev = torch.from_numpy(frames).cuda()
+    ctx.set_camera(sc0.K, sc0.D); ctx.set_params(sc0.params); ctx.set_markers(sc0.markers)
+    ctx.streams_reset(S)
+    ctx.streams_set_frame_map(0, 0)
+    out = []
+    for t in range(T):
+        res = ctx.streams_step_device(dev[t].data_ptr(), W, W * H, W, H, [streams[s].times[t] for s in range(S)])
+        out.append(results_to_arrays(res).copy())
+    return out
+
+
+def test_streams_match_oracle_frame_by_frame(gpu_ctx_752):
+    import torch
+    T = 22
+    streams = [synth.make_stream_scene(T, n_leds=5, seed=300 + s) for s in range(6)]
+    # stream 1: the LEDs vanish for two frames (ROI search fails, whole-image retry fails), then come back
+    streams[1].frames[9][:] = 0
+    streams[1].frames[10][:] = 0
+    # stream 2: one LED is occluded for a while (4 detections, NN correspondences still fine)
+    for t in range(6, 12):
+        px, _, _ = synth.project_distorted(streams[2].K, streams[2].D, streams[2].poses[t], streams[2].markers)
+        x, y = int(px[0][0]), int(px[0][1])
+        streams[2].frames[t][max(y - 12, 0):y + 12, max(x - 12, 0):x + 12] = 0
+    # stream 3: a jump (frames of another trajectory spliced in) breaks the prediction: NN check fails -> re-initialise
+    other = synth.make_stream_scene(T, n_leds=5, seed=999)
+    for t in range(12, T):
+        streams[3].frames[t] = other.frames[t]
+    out = _run(streams, gpu_ctx_752, torch)
+    n_upd = n_retry = n_reinit = 0
+    for s, sc in enumerate(streams):
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        for t in range(T):
+            upd = est.estimate_body_pose(sc.frames[t], sc.times[t])
+            r = out[t][s]
+            tag = f"stream {s} frame {t}"
+            assert bool(r["updated"]) == upd, tag
+            assert tuple(r["roi"]) == tuple(est.region_of_interest), (tag, tuple(r["roi"]), est.region_of_interest)
+            n_retry += int(bool(r["flags"] & 16)); n_reinit += int(bool(r["flags"] & 8) and t > 0)
+            if upd:
+                n_upd += 1
+                k = r["n_corr"]
+                assert np.array_equal(r["corr"][:2 * k].reshape(k, 2), est.correspondences()), tag
+                dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+                assert dt < 1e-6 and dr < 1e-6, (tag, dt, dr)
+                assert r["gn_iters"] == est.gn_iterations(), tag
+                co = est.covariance()
+                assert np.allclose(r["cov"].reshape(6, 6), co, rtol=1e-6, atol=1e-12 * np.abs(co).max()), tag
+    assert n_upd >= 0.8 * len(streams) * T
+    assert n_retry >= 2          # the blanked frames forced whole-image retries
+    assert n_reinit >= 1         # the spliced trajectory forced a brute-force re-initialisation while tracking
+
+
+def test_streams_with_frame_map_replay(gpu_ctx_752):
+    """Many streams replaying a few recorded sequences through the frame map give identical results per replica."""
+    import torch
+    T, Sd, rep = 8, 3, 4
+    seqs = [synth.make_stream_scene(T, n_leds=5, seed=700 + s) for s in range(Sd)]
+    H, W = seqs[0].height, seqs[0].width
+    buf = torch.from_numpy(np.stack([f for sc in seqs for f in sc.frames])).cuda()               # (Sd*T) x H x W
+    ctx = gpu_ctx_752
+    ctx.set_camera(seqs[0].K, seqs[0].D); ctx.set_params(seqs[0].params); ctx.set_markers(seqs[0].markers)
+    S = Sd * rep
+    ctx.streams_reset(S)
+    for t in range(T):
+        fmap = torch.tensor([(s % Sd) * T + t for s in range(S)], dtype=torch.int32, device="cuda")
+        ctx.streams_set_frame_map(fmap.data_ptr(), Sd * T)
+        res = results_to_arrays(ctx.streams_step_device(buf.data_ptr(), W, W * H, W, H, [seqs[s % Sd].times[t] for s in range(S)]))
+        for s in range(Sd, S):
+            a, b = res[s], res[s % Sd]
+            assert a["updated"] == b["updated"] and np.array_equal(a["pose"], b["pose"]) and tuple(a["roi"]) == tuple(b["roi"])
+    ctx.streams_set_frame_map(0, 0)
+    assert res["updated"].sum() == S
