@@ -195,6 +195,57 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ tracking mode (secondary)
+def run_tracking(args):
+    """Steady-state tracking throughput: S streams, each an independent PoseEstimator whose
+    state lives on the GPU; one step = one frame for every stream (mpe_streams_step_device).  Sd distinct synthetic
+    trajectories of T frames are replayed by S = Sd * rep streams through the frame map; per step Sd distinct frames
+    (> L2 for the default sizes) are read.  Single GPU; prints one JSON line (not the headline metric)."""
+    import torch
+    import rpg_monocular_pose_estimator_b200 as mpe
+    from rpg_monocular_pose_estimator_b200 import synth
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    W, H = args.width, args.height
+    Sd, T = 512, 8 + args.warmup + args.steps
+    S = args.batch
+    seqs = [synth.make_stream_scene(T, n_leds=args.leds, width=W, height=H, seed=args.seed + 17 * s) for s in range(Sd)]
+    buf = torch.from_numpy(np.stack([f for sc in seqs for f in sc.frames])).to(dev)          # (Sd*T) x H x W
+    ctx = mpe.Context(0, S, W, H)
+    ctx.set_camera(seqs[0].K, seqs[0].D); ctx.set_params(seqs[0].params); ctx.set_markers(seqs[0].markers)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    ctx.streams_reset(S)
+    base = (torch.arange(S, dtype=torch.int32, device=dev) % Sd) * T
+    fmaps = [(base + t).contiguous() for t in range(T)]
+    times = [np.full(S, t / 60.0) for t in range(T)]
+    def step(t, fetch=False):
+        ctx.streams_set_frame_map(fmaps[t].data_ptr(), Sd * T)
+        return ctx.streams_step_device(buf.data_ptr(), W, W * H, W, H, times[t], fetch=fetch)
+    t = 0
+    for _ in range(8 + args.warmup):          # cold start + settle into tracking (it_since_initialized_ == 2), untimed
+        step(t); t += 1
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(t); t += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    res = results_to_arrays(ctx.fetch_results(S))
+    line = {"metric": f"frames/sec ({W}x{H}, {args.leds} LEDs, tracking mode, device-resident streams)", "value": S / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 + f64", "data": "synthetic",
+            "config": {"workload": f"{S} streams ({Sd} distinct trajectories replayed), one frame per stream per step, ROI search + NN correspondences + checkCorrespondences + optimisePose",
+                       "streams_updated_last_step": int(res["updated"].sum()), "mean_roi_pixels": float(np.mean(res["roi"][:, 2] * res["roi"][:, 3])),
+                       "reinitialised_last_step": int(np.sum((res["flags"] & 8) != 0))},
+            "gpu_launches": ctx.launch_count() - l0}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -207,6 +258,8 @@ def main():
     ap.add_argument("--leds", type=int, default=N_LEDS)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--mode", default="cold", choices=["cold", "tracking"],
+                    help="cold (headline): every frame runs the full pipeline; tracking: device-resident streams with ROI search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -214,6 +267,9 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.mode == "tracking":
+        run_tracking(args)
         return
 
     import torch
