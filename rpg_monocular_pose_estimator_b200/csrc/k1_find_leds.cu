@@ -142,11 +142,12 @@ __host__ __device__ inline size_t k1_ring_offset() {
   return (off + 1023) & ~(size_t)1023;
 }
 
-template <int R, bool kLowThr, int kStages>
+template <bool kLowThr, int kStages>
 __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_constant__ CUtensorMap tmap, const K1aArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const K1Geom& g = a.g;
-  constexpr int kRows = kTileRows + 2 * R;
+  const int R = a.radius;
+  const int kRows = kTileRows + 2 * R;
   const int box_w = g.box_w;                       // u32 per smem row
   const uint32_t stage_bytes = (uint32_t)(kRows * box_w * 4);          // bytes one TMA box delivers
   const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;           // TMA destinations must be 128-byte aligned
@@ -272,8 +273,11 @@ __device__ __forceinline__ int blur_smem_words(int box_w, int tw_px) {
   return 4 + kTileRows * ((box_w + 31) >> 5) + kTileRows * ((tw_px + 31) >> 5);
 }
 
-template <int R>
+template <int RT>   // RT > 0: radius known at compile time (fully unrolled); RT == 0: a.radius, generic loops (R up to kMaxRadius)
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
+  const int R = (RT > 0) ? RT : a.radius;
+  constexpr int kR = (RT > 0) ? RT : kMaxRadius;     // array bounds
+  const int dj_max = (R + 3) >> 2;                    // source words that can influence an output word: j-dj_max .. j+dj_max
   extern __shared__ __align__(16) uint8_t bsm[];
   const K1Geom& g = a.g;
   const int box_w = g.box_w;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
         const uint32_t e = a.pool[rec.z + t];
         const int row = (int)(e >> 8), j = (int)(e & 0xff);
         const int r_lo = max(row - 2 * R, 0), r_hi = min(row, out_rows - 1);
-        for (int jj = max(j - 1, 0); jj <= min(j + 1, box_w - 1); ++jj) {
+        for (int jj = max(j - dj_max, 0); jj <= min(j + dj_max, box_w - 1); ++jj) {
           const uint32_t bit = 1u << (jj & 31);
           for (int r = r_lo; r <= r_hi; ++r) atomicOr(&act[r * hot_wpr + (jj >> 5)], bit);
         }
@@ -345,10 +349,10 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
       const int Y = y0 + R + r;                                        // image row of this output row
       const bool interior = (first_px - R >= c.roi.x) && (first_px + 3 + R < c.roi.x + c.roi.w) &&
                             (Y - R >= c.roi.y) && (Y + R < c.roi.y + c.roi.h);
-      uint32_t hsum[2 * R + 1][4];
+      uint32_t hsum[2 * kR + 1][4];
 #pragma unroll
       for (int dr = 0; dr <= 2 * R; ++dr) {
-        uint32_t px[4 + 2 * R];
+        uint32_t px[4 + 2 * kR];
         if (interior) {
           const uint8_t* src = frame + (size_t)(Y + dr - R) * a.pitch + (first_px - R);
 #pragma unroll
@@ -420,10 +424,10 @@ size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages) {
   return k1_ring_offset() + (size_t)stages * stage_stride;
 }
 
-template <int R, bool kLow, int kStages>
+template <bool kLow, int kStages>
 static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
-  size_t smem = find_leds_smem_bytes(a.g, R, kStages);
-  auto kern = scan_kernel<R, kLow, kStages>;
+  size_t smem = find_leds_smem_bytes(a.g, a.radius, kStages);
+  auto kern = scan_kernel<kLow, kStages>;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -438,24 +442,22 @@ static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, i
   return cudaGetLastError();
 }
 
-template <int R>
-static cudaError_t launch_k1_r(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
+static cudaError_t launch_scan(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
   // ring depth: as many stages as fit in ~110 KB so that two CTAs share an SM
+  const int R = a.radius;
   size_t s4 = find_leds_smem_bytes(a.g, R, 4), s3 = find_leds_smem_bytes(a.g, R, 3);
   bool low = a.threshold < 128;
-  cudaError_t e;
-  if (s4 <= 110 * 1024) e = low ? launch_scan_inst<R, true, 4>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 4>(a, tmap, n_sms, st);
-  else if (s3 <= 110 * 1024) e = low ? launch_scan_inst<R, true, 3>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 3>(a, tmap, n_sms, st);
-  else e = low ? launch_scan_inst<R, true, 2>(a, tmap, n_sms, st) : launch_scan_inst<R, false, 2>(a, tmap, n_sms, st);
-  return e;
+  if (s4 <= 110 * 1024) return low ? launch_scan_inst<true, 4>(a, tmap, n_sms, st) : launch_scan_inst<false, 4>(a, tmap, n_sms, st);
+  if (s3 <= 110 * 1024) return low ? launch_scan_inst<true, 3>(a, tmap, n_sms, st) : launch_scan_inst<false, 3>(a, tmap, n_sms, st);
+  return low ? launch_scan_inst<true, 2>(a, tmap, n_sms, st) : launch_scan_inst<false, 2>(a, tmap, n_sms, st);
 }
 
-template <int R>
+template <int RT>
 static cudaError_t launch_blur_r(const K1aArgs& a, int n_sms, cudaStream_t st) {
   size_t bsmem = (size_t)(4 + kTileRows * ((a.g.box_w + 31) >> 5) + kTileRows * ((a.g.tw_px + 31) >> 5)) * 4 + (size_t)kTileRows * a.g.box_w * 2;
   int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
   int grid = n_tiles < n_sms * 8 ? n_tiles : n_sms * 8;
-  blur_kernel<R><<<grid, kBlurThreads, bsmem, st>>>(a);
+  blur_kernel<RT><<<grid, kBlurThreads, bsmem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -465,18 +467,13 @@ cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStrea
     case 2: return launch_blur_r<2>(a, n_sms, st);
     case 3: return launch_blur_r<3>(a, n_sms, st);
     case 4: return launch_blur_r<4>(a, n_sms, st);
-    default: return cudaErrorInvalidValue;
+    default: return (radius >= 1 && radius <= kMaxRadius) ? launch_blur_r<0>(a, n_sms, st) : cudaErrorInvalidValue;
   }
 }
 
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st) {
-  switch (radius) {
-    case 1: return launch_k1_r<1>(a, tmap, n_sms, st);
-    case 2: return launch_k1_r<2>(a, tmap, n_sms, st);
-    case 3: return launch_k1_r<3>(a, tmap, n_sms, st);
-    case 4: return launch_k1_r<4>(a, tmap, n_sms, st);
-    default: return cudaErrorInvalidValue;
-  }
+  if (radius < 1 || radius > kMaxRadius || radius != a.radius) return cudaErrorInvalidValue;
+  return launch_scan(a, tmap, n_sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------

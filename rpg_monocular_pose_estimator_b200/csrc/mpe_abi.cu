@@ -221,6 +221,7 @@ int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, 
   if (T < 0) T = 0;                  // THRESH_TOZERO with a negative threshold keeps every pixel; so does "> 0" (0 stays 0)
   if (T > 255) T = 255;              // nothing is > 255
   a.threshold = T;
+  a.radius = radius;
   a.thr_k = (T < 128) ? (127 - T) * 0x01010101 : (255 - T) * 0x01010101;
   a.rowflags = c->d.rowflags + (size_t)slot0 * c->flags_per_frame;
   a.mask = c->d.mask + (size_t)slot0 * c->max_h * c->mask_wpr;
@@ -516,7 +517,7 @@ int mpe_set_params(mpe_ctx* c, const mpe_params* p) {
   int radius;
   uint32_t taps[kMaxTaps];
   if (!gaussian_taps_8u(p->gaussian_sigma, &radius, taps))
-    return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "] (sigma in about (0.09, 1.41))");
+    return fail(c, MPE_E_UNSUPPORTED, "gaussian_sigma must give a kernel radius in [1, " + std::to_string(kMaxRadius) + "] (sigma in about (0.09, 6.08))");
   c->params = *p;
   c->pp.back_projection_pixel_tolerance = p->back_projection_pixel_tolerance;
   c->pp.back_proj_sq_max = sqrt_less_than_bound(p->back_projection_pixel_tolerance);

@@ -8,7 +8,8 @@
 namespace mpe {
 
 constexpr int kTileRows = 32;        // output rows per K1 tile (= bits of one row-flag word)
-constexpr int kMaxRadius = 4;        // largest Gaussian radius the fused kernel is instantiated for
+constexpr int kMaxRadius = 18;       // largest Gaussian radius (sigma 6 -> ksize 37, the reference's dynamic_reconfigure maximum)
+constexpr int kMaxUnrolledRadius = 4; // radii with a fully unrolled blur instantiation; larger ones run the generic loop
 constexpr int kMaxTaps = 2 * kMaxRadius + 1;
 constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
 constexpr int kK1Threads = 256;
@@ -58,6 +59,7 @@ struct K1aArgs {
   K1Geom g;
   int thr_k;                 // SWAR constant for "any byte > threshold"
   int threshold;
+  int radius;                // Gaussian radius R (taps = 2R+1)
   uint32_t taps[kMaxTaps];   // 8.8 fixed-point Gaussian taps, sum = 256
   uint32_t* rowflags;        // [n_frames][flags_per_frame]   zeroed before the launch; K1c writes the hot tiles' words
   uint32_t* mask;            // [n_frames][mask_rows][mask_wpr]

@@ -59,7 +59,7 @@ def test_roi_subrects_and_border_blobs(gpu_ctx_752):
     assert total > 30
 
 
-@pytest.mark.parametrize("sigma", [0.3, 0.45, 0.6, 0.8, 1.0, 1.2, 1.4])
+@pytest.mark.parametrize("sigma", [0.3, 0.45, 0.6, 0.8, 1.0, 1.2, 1.4, 1.5, 2.0, 3.0, 6.0])
 def test_other_sigmas(gpu_ctx_752, sigma):
     rng = np.random.default_rng(int(sigma * 100))
     K, D = synth.camera()
