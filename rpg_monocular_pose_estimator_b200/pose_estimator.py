@@ -80,6 +80,18 @@ class Context:
                                         ce.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n), C.byref(fl)))
         return px[:n.value].copy(), ce[:n.value].copy(), fl.value
 
+    def find_leds_strided(self, image: np.ndarray, roi):
+        """Like find_leds but takes a row-strided (non-contiguous) uint8 view as is: pitch = image.strides[0]."""
+        assert image.dtype == np.uint8 and image.strides[1] == 1
+        h, w = image.shape
+        px = np.zeros((MPE_MAX_BLOBS, 2), np.float64)
+        ce = np.zeros((MPE_MAX_BLOBS, 2), np.float32)
+        n, fl = C.c_int(0), C.c_int(0)
+        r = MpeRect(int(roi[0]), int(roi[1]), int(roi[2]), int(roi[3]))
+        self.check(self.L.mpe_find_leds(self.h, C.c_void_p(image.ctypes.data), image.strides[0], w, h, r, _dp(px),
+                                        ce.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n), C.byref(fl)))
+        return px[:n.value].copy(), ce[:n.value].copy(), fl.value
+
     def initialise(self, det):
         det = np.ascontiguousarray(det, np.float64).reshape(-1, 2)
         hist = np.zeros((len(det), self.n_obj), np.uint32)

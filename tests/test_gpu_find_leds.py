@@ -114,3 +114,44 @@ def test_1080p_two_column_tiles():
             _compare(ctx, img, roi, p, K, D, f"1080p random it{it}")
     finally:
         ctx.close()
+
+
+def test_odd_image_sizes_and_pitch():
+    """Widths that are not multiples of 4/16/32 and a padded host pitch: the device copy is pitched to 16 bytes and the
+    tensor map sees the padded row; results must not depend on what lies in the padding."""
+    import rpg_monocular_pose_estimator_b200 as mpe
+    rng = np.random.default_rng(17)
+    for (w, h) in [(750, 470), (641, 479), (333, 97), (67, 33)]:
+        ctx = mpe.Context(0, 2, w, h)
+        try:
+            K, D = synth.camera(w, h)
+            p = synth.Params(min_blob_area=1.0, max_blob_area=5000, max_width_height_distortion=0.95, max_circular_distortion=0.99)
+            for it in range(4):
+                big = random_blob_image(rng, h, w + 13, n_blobs=20, kind="mixed")
+                img = big[:, :w] if it % 2 else np.ascontiguousarray(big[:, :w])     # odd iterations: non-contiguous rows (pitch = w + 13)
+                roi = (0, 0, w, h) if it < 2 else (3, 2, w - 5, h - 3)
+                ctx.set_camera(K, D); ctx.set_params(p)
+                px, centers, flags = ctx.find_leds_strided(img, roi)
+                opx, ocenters = oracle_find_leds(np.ascontiguousarray(img), roi, p, K, D)
+                assert flags == 0 and len(centers) == len(ocenters), (w, h, it)
+                if len(ocenters):
+                    assert np.array_equal(centers.view(np.uint32), ocenters.view(np.uint32)) and np.array_equal(px, opx), (w, h, it)
+        finally:
+            ctx.close()
+
+
+def test_error_codes(gpu_ctx_752):
+    import rpg_monocular_pose_estimator_b200 as mpe
+    K, D = synth.camera()
+    gpu_ctx_752.set_camera(K, D)
+    with pytest.raises(mpe.MpeError):                      # sigma beyond the largest supported radius
+        gpu_ctx_752.set_params(synth.Params(gaussian_sigma=7.0))
+    gpu_ctx_752.set_params(synth.Params())
+    img = np.zeros((480, 752), np.uint8)
+    with pytest.raises(mpe.MpeError):                      # ROI outside the image: cv::Mat::operator() would throw in the reference
+        gpu_ctx_752.find_leds(img, (700, 0, 100, 100))
+    with pytest.raises(mpe.MpeError):                      # larger than the context was created for
+        gpu_ctx_752.find_leds(np.zeros((481, 752), np.uint8), (0, 0, 10, 10))
+    with pytest.raises(mpe.MpeError):
+        gpu_ctx_752.set_camera(K, np.zeros(3))             # 3 distortion coefficients is not a model OpenCV accepts either
+    gpu_ctx_752.set_camera(K, D)
