@@ -30,7 +30,7 @@ struct DevBuffers {
   double* det = nullptr;           // [max_batch][MPE_MAX_BLOBS][2]
   float* centers = nullptr;        // [max_batch][MPE_MAX_BLOBS][2]
   uint32_t* hist = nullptr;        // [max_batch][MPE_MAX_DET*MPE_MAX_LEDS]
-  uint32_t* done = nullptr;        // [max_batch]
+  double* bearings = nullptr;      // [max_batch][MPE_MAX_DET][3]
   uint32_t* corr = nullptr;        // [max_batch][2*MPE_MAX_LEDS]
   int* n_corr = nullptr;           // [max_batch]
   double* pose = nullptr;          // [max_batch][16]
@@ -284,17 +284,16 @@ int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* acti
   k.pp = c->pp;
   k.split = choose_split(c, n);
   k.hist = c->d.hist + (size_t)slot0 * MPE_MAX_DET * MPE_MAX_LEDS;
-  k.done_counter = c->d.done + slot0;
+  k.bearings = c->d.bearings + (size_t)slot0 * MPE_MAX_DET * 3;
   k.corr = c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS;
   k.n_corr = c->d.n_corr + slot0;
   k.frame_flags = c->d.flags + slot0;
   k.active = active;
   CUDA_TRY(c, cudaMemsetAsync(k.hist, 0, (size_t)n * MPE_MAX_DET * MPE_MAX_LEDS * sizeof(uint32_t), st));
-  CUDA_TRY(c, cudaMemsetAsync(k.done_counter, 0, (size_t)n * sizeof(uint32_t), st));
   time_begin(c, 2, st);
-  CUDA_TRY(c, launch_p3p_sweep(k, st));
+  CUDA_TRY(c, launch_p3p_sweep(k, c->n_sms, st));
   time_end(c, 2, st);
-  ++c->launches;
+  c->launches += 3;
   return MPE_OK;
 }
 
@@ -424,7 +423,7 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.det, B * MPE_MAX_BLOBS * 2));
   CREATE_TRY(dev_alloc(&c->d.centers, B * MPE_MAX_BLOBS * 2));
   CREATE_TRY(dev_alloc(&c->d.hist, B * MPE_MAX_DET * MPE_MAX_LEDS));
-  CREATE_TRY(dev_alloc(&c->d.done, B));
+  CREATE_TRY(dev_alloc(&c->d.bearings, B * MPE_MAX_DET * 3));
   CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.n_corr, B));
   CREATE_TRY(dev_alloc(&c->d.pose, B * 16));
@@ -472,7 +471,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
-  cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.done); cudaFree(c->d.corr);
+  cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.bearings); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
   cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
   cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);

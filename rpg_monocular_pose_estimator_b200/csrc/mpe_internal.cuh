@@ -96,7 +96,7 @@ struct K2Args {
   DevPoseParams pp;
   int split;                 // CTAs per frame
   uint32_t* hist;            // [n_frames][MPE_MAX_DET*MPE_MAX_LEDS], zeroed before launch
-  uint32_t* done_counter;    // [n_frames], zeroed before launch
+  double* bearings;          // [n_frames][MPE_MAX_DET][3] image_vectors_ (written by the prologue kernel)
   uint32_t* corr;            // [n_frames][2*MPE_MAX_LEDS]
   int* n_corr;               // [n_frames]
   int* frame_flags;          // [n_frames] in/out
@@ -159,7 +159,7 @@ cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st);
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);
-cudaError_t launch_p3p_sweep(const K2Args& a, cudaStream_t st);
+cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st);
 cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st);
 cudaError_t launch_p3p_batch(const double* f, const double* P, int n, double* sol, int* status, cudaStream_t st);
 size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages);
