@@ -217,10 +217,11 @@ def run_tracking(args):
     stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
     ctx.streams_reset(S)
     base = (torch.arange(S, dtype=torch.int32, device=dev) % Sd) * T
-    fmaps = [(base + t).contiguous() for t in range(T)]
+    fmap = base.clone()                       # one buffer, advanced in place: a stable key lets the step replay as a CUDA graph
     times = [np.full(S, t / 60.0) for t in range(T)]
+    ctx.streams_set_frame_map(fmap.data_ptr(), Sd * T)
     def step(t, fetch=False):
-        ctx.streams_set_frame_map(fmaps[t].data_ptr(), Sd * T)
+        fmap.copy_(base + t)
         return ctx.streams_step_device(buf.data_ptr(), W, W * H, W, H, times[t], fetch=fetch)
     t = 0
     for _ in range(8 + args.warmup):          # cold start + settle into tracking (it_since_initialized_ == 2), untimed
@@ -246,6 +247,92 @@ def run_tracking(args):
     ctx.close()
 
 
+# ------------------------------------------------------------------------------------------------ single-camera latency (secondary)
+def run_latency(args):
+    """What ONE camera sees (the way MPENode drives the reference: one image per callback, monocular_pose_estimator.cpp:133-159):
+    per-image wall-clock latency of mpe_streams_step(n_streams=1) — H2D of the whole image, the tracking step replayed as one CUDA
+    graph, D2H of the result record, synchronise — against the CPU oracle's estimateBodyPose on the same sequence, same host."""
+    import torch
+    import rpg_monocular_pose_estimator_b200 as mpe
+    from rpg_monocular_pose_estimator_b200 import synth
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    from oracle import pose_oracle
+    import cv2
+    cv2.setNumThreads(1)
+    W, H = args.width, args.height
+    T = 40 + args.steps * 20
+    sc = synth.make_stream_scene(T, n_leds=args.leds, width=W, height=H, seed=args.seed)
+    out = {}
+    for label, frames in (("pinned", torch.from_numpy(sc.frames).pin_memory().numpy()), ("pageable", sc.frames)):
+        for graphs in (True, False):
+            ctx = mpe.Context(0, 1, W, H)
+            ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
+            ctx.set_graph_replay(graphs)
+            ctx.streams_reset(1)
+            res = (mpe.MpeResult * 1)()
+            tarr = np.zeros(1)
+            tp = tarr.ctypes.data_as(C.POINTER(C.c_double))
+            L, h = ctx.L, ctx.h
+            lat, upd = [], 0
+            l0 = ctx.launch_count()
+            for t in range(T):
+                tarr[0] = sc.times[t]
+                ptr = C.c_void_p(frames[t].ctypes.data)
+                t0 = time.perf_counter()
+                rc = L.mpe_streams_step(h, ptr, W, W * H, W, H, 1, tp, res)
+                t1 = time.perf_counter()
+                assert rc == 0
+                upd += res[0].updated
+                if t >= 40:
+                    lat.append((t1 - t0) * 1e6)
+            lat = np.array(lat)
+            out[f"{label}_{'graph' if graphs else 'launches'}"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
+                                                                    "mean_us": float(lat.mean()), "frames_updated": upd, "frames": T,
+                                                                    "gpu_launches_per_frame": (ctx.launch_count() - l0) / T}
+            ctx.close()
+    # cameras per call: n independent streams advanced by ONE mpe_streams_step (host images in, host records out)
+    sweep = []
+    for n in (1, 2, 4, 8, 16, 64, 256):
+        ctx = mpe.Context(0, n, W, H)
+        ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
+        ctx.streams_reset(n)
+        Tn = min(T, 120)
+        hb = torch.empty((n, H, W), dtype=torch.uint8).pin_memory().numpy()
+        res = (mpe.MpeResult * n)()
+        tarr = np.zeros(n)
+        tp = tarr.ctypes.data_as(C.POINTER(C.c_double))
+        ptr = C.c_void_p(hb.ctypes.data)
+        lat = []
+        for t in range(Tn):
+            hb[:] = sc.frames[t]                    # every camera sees the same sequence (results are per stream anyway)
+            tarr[:] = sc.times[t]
+            t0 = time.perf_counter()
+            rc = ctx.L.mpe_streams_step(ctx.h, ptr, W, W * H, W, H, n, tp, res)
+            t1 = time.perf_counter()
+            assert rc == 0
+            if t >= 20:
+                lat.append((t1 - t0) * 1e6)
+        assert all(res[i].updated for i in range(n))
+        p50 = float(np.percentile(lat, 50))
+        sweep.append({"cameras_per_call": n, "p50_us_per_call": p50, "us_per_image": p50 / n, "images_per_s": n / (p50 * 1e-6)})
+        ctx.close()
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    lat = []
+    for t in range(T):
+        t0 = time.perf_counter()
+        est.estimate_body_pose(sc.frames[t], sc.times[t])
+        t1 = time.perf_counter()
+        if t >= 40:
+            lat.append((t1 - t0) * 1e6)
+    lat = np.array(lat)
+    cpu = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "mean_us": float(lat.mean()), "cores": 1, "kind": "port"}
+    best = out["pinned_graph"]
+    line = {"metric": f"single-camera latency per image ({W}x{H}, {args.leds} LEDs, tracking mode)", "value": best["p50_us"], "unit": "us",
+            "n_gpus": 1, "higher_is_better": False, "data": "synthetic", "variants": out, "cameras_per_call_sweep": sweep, "cpu_baseline": cpu,
+            "config": {"workload": f"one stream, {T} consecutive frames, one mpe_streams_step call per image (whole image H2D + graph replay + result D2H + sync)"}}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -258,7 +345,7 @@ def main():
     ap.add_argument("--leds", type=int, default=N_LEDS)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--mode", default="cold", choices=["cold", "tracking"],
+    ap.add_argument("--mode", default="cold", choices=["cold", "tracking", "latency"],
                     help="cold (headline): every frame runs the full pipeline; tracking: device-resident streams with ROI search")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -270,6 +357,9 @@ def main():
         return
     if args.mode == "tracking":
         run_tracking(args)
+        return
+    if args.mode == "latency":
+        run_latency(args)
         return
 
     import torch

@@ -180,6 +180,16 @@ int mpe_streams_set_frame_map(mpe_ctx* ctx, const int* frame_index_device, int n
 int mpe_streams_step_device(mpe_ctx* ctx, const uint8_t* frames_device, int pitch, long long frame_stride,
                             int width, int height, int n_streams, const double* times, mpe_result* results);
 
+/* Host-image variant of the tracking step — the per-image call of a camera driver (MPENode::imageCallback ->
+ * PoseEstimator::estimateBodyPose, monocular_pose_estimator.cpp:133-159): frames are n_streams images in HOST memory
+ * (image s belongs to stream s; `pitch` bytes per row, `frame_stride` bytes between images), copied to the GPU inside
+ * the call; results (HOST, required) are valid on return.  With n_streams = 1 this is a drop-in estimateBodyPose whose
+ * PoseEstimator state lives on the GPU.  From its second use with unchanged geometry/configuration the step is replayed
+ * as ONE CUDA graph launch (about 30 kernel/memset nodes); mpe_set_graph_replay(ctx, 0) forces plain launches. */
+int mpe_streams_step(mpe_ctx* ctx, const uint8_t* frames, int pitch, long long frame_stride, int width, int height,
+                     int n_streams, const double* times, mpe_result* results);
+int mpe_set_graph_replay(mpe_ctx* ctx, int on);
+
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* When enabled, the batch entry points bracket each kernel with CUDA events on the launching stream.
  * mpe_get_kernel_times returns, for the last synchronised batch, milliseconds per stage:

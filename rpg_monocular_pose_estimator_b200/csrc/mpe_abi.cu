@@ -80,6 +80,22 @@ struct mpe_ctx {
   const int* frame_map = nullptr;   // optional stream -> image index table for mpe_streams_step_device
   int frame_map_total = 0;
   std::vector<cudaEvent_t> chunk_events;
+  // CUDA-graph replay of the tracking step (mpe_streams_step*): the ~30 small launches of one step become one graph launch
+  bool use_graphs = true;
+  unsigned long long cfg_version = 0;     // bumped by every configuration call; a stale graph is rebuilt
+  struct StepGraphKey {
+    const uint8_t* frames; int pitch; long long stride; int w, h, n; const int* fmap; int fmap_total; int fetch;
+    unsigned long long cfg; cudaStream_t st;
+    bool operator==(const StepGraphKey& o) const {
+      return frames == o.frames && pitch == o.pitch && stride == o.stride && w == o.w && h == o.h && n == o.n && fmap == o.fmap &&
+             fmap_total == o.fmap_total && fetch == o.fetch && cfg == o.cfg && st == o.st;
+    }
+  };
+  StepGraphKey graph_key{}, pending_key{};   // a key is run eagerly once (function attributes get configured), captured on its second use
+  bool have_pending = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0;           // kernel launches contained in one replay
+  long long graph_replays = 0;
 };
 
 namespace {
@@ -478,6 +494,7 @@ void mpe_destroy(mpe_ctx* c) {
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -499,6 +516,7 @@ int mpe_set_camera(mpe_ctx* c, const double K[9], const double* D, int nD) {
   for (int i = 0; i < MPE_MAX_DIST; ++i) c->cam.D[i] = (i < nD) ? D[i] : 0.0;
   c->cam.nD = nD;
   c->have_camera = true;
+  ++c->cfg_version;
   return MPE_OK;
 }
 
@@ -508,6 +526,7 @@ int mpe_set_markers(mpe_ctx* c, const double* xyz, int n) {
   for (int i = 0; i < 3 * n; ++i) c->pp.markers[i] = xyz[i];
   c->pp.histogram_threshold = (n >= 3) ? num_combinations_ref((unsigned)n, 3u) : 0u;   // pose_estimator.cpp:54
   c->have_markers = true;
+  ++c->cfg_version;
   return MPE_OK;
 }
 
@@ -524,10 +543,11 @@ int mpe_set_params(mpe_ctx* c, const mpe_params* p) {
   c->pp.certainty_threshold = p->certainty_threshold;
   c->pp.valid_correspondence_threshold = p->valid_correspondence_threshold;
   c->have_params = true;
+  ++c->cfg_version;
   return MPE_OK;
 }
 
-int mpe_set_histogram_threshold(mpe_ctx* c, uint32_t t) { if (!c) return MPE_E_INVALID; c->pp.histogram_threshold = t; return MPE_OK; }
+int mpe_set_histogram_threshold(mpe_ctx* c, uint32_t t) { if (!c) return MPE_E_INVALID; c->pp.histogram_threshold = t; ++c->cfg_version; return MPE_OK; }
 uint32_t mpe_get_histogram_threshold(const mpe_ctx* c) { return c ? c->pp.histogram_threshold : 0u; }
 
 int mpe_synchronize(mpe_ctx* c) {
@@ -774,18 +794,9 @@ int mpe_streams_set_frame_map(mpe_ctx* c, const int* frame_index_device, int n_f
   return MPE_OK;
 }
 
-// One estimateBodyPose step for n_streams independent PoseEstimators (pose_estimator.cpp:62-147) without a host round trip.
-int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch, long long frame_stride, int width, int height,
-                            int n_streams, const double* times, mpe_result* results) {
-  int rc = check_configured(c, true);
-  if (rc != MPE_OK) return rc;
-  if (!frames_device || !times || n_streams < 1) return MPE_E_INVALID;
-  if (n_streams > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "streams or image larger than the context capacity");
-  if (c->cam.nD < 5) return fail(c, MPE_E_UNSUPPORTED, "LEDDetector::distortPoints reads five distortion coefficients (led_detector.cpp:190-194)");
-  CUDA_TRY(c, cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
-  const int n = n_streams;
-  CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+// Enqueues one estimateBodyPose step (pose_estimator.cpp:62-147) for n streams on `st`; the time stamps are already in c->d.times.
+static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st) {
+  const int width = src.width, height = src.height;
   const size_t B = (size_t)c->max_batch;
   TrackArgs t{};
   t.n = n; t.img_w = width; t.img_h = height; t.roi_border = c->params.roi_border_thickness;
@@ -796,10 +807,8 @@ int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch,
   t.track_flags = c->d.track_flags;
   t.n_det = c->d.n_det; t.flags = c->d.flags; t.det = c->d.det; t.centers = c->d.centers;
   t.corr = c->d.corr; t.n_corr = c->d.n_corr; t.pose_io = c->d.pose; t.cov = c->d.cov; t.ok = c->d.ok; t.iters = c->d.iters; t.updated = c->d.updated;
-  const int total = c->frame_map ? c->frame_map_total : n;
-  FrameSource src{frames_device, pitch, frame_stride, width, height, total};
   Roi full{0, 0, width, height};
-
+  int rc;
   CUDA_TRY(c, launch_track_begin(t, st));                                                        // predictWithROI
   rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, nullptr);   // findLeds(ROI)
   if (rc != MPE_OK) return rc;
@@ -820,9 +829,112 @@ int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch,
   if (rc != MPE_OK) return rc;
   CUDA_TRY(c, launch_track_finish(t, c->d.results, st));
   c->launches += 7;
-  if (results) return mpe_fetch_results(c, n, results);
   return MPE_OK;
 }
+
+// The step as one CUDA-graph replay: captured once per (frame buffer, geometry, configuration) key, then a single
+// cudaGraphLaunch replaces ~30 kernel/memset launches — what makes a one-camera, one-image-at-a-time caller (the way MPENode
+// drives the reference, monocular_pose_estimator.cpp:133-159) latency-competitive.  Per-kernel event timing disables replay.
+static int run_streams_step(mpe_ctx* c, const FrameSource& src, int n, const double* times, bool fetch) {
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (!c->use_graphs || c->timing) {
+    int rc = enqueue_streams_step(c, src, n, st);
+    if (rc != MPE_OK) return rc;
+    if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
+    return MPE_OK;
+  }
+  mpe_ctx::StepGraphKey key{src.base, src.pitch, src.frame_stride, src.width, src.height, n, c->frame_map, c->frame_map_total, fetch ? 1 : 0,
+                            c->cfg_version, st};
+  if (!c->graph_exec || !(key == c->graph_key)) {
+    if (!c->have_pending || !(key == c->pending_key)) {      // first use of this key: plain launches
+      c->pending_key = key; c->have_pending = true;
+      int rc = enqueue_streams_step(c, src, n, st);
+      if (rc != MPE_OK) return rc;
+      if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
+      return MPE_OK;
+    }
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    const long long l0 = c->launches;
+    CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_streams_step(c, src, n, st);
+    cudaError_t ce = cudaSuccess;
+    if (rc == MPE_OK && fetch) ce = cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st);
+    cudaGraph_t g = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(st, &g);
+    if (rc != MPE_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess || ee != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      return fail(c, MPE_E_CUDA, std::string("stream capture of the tracking step failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+    }
+    cudaError_t ie = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { c->graph_exec = nullptr; return fail(c, MPE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    c->graph_launches = c->launches - l0;
+    c->launches = l0;                        // nothing ran during the capture
+    c->graph_key = key;
+  }
+  CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
+  c->launches += c->graph_launches;
+  ++c->graph_replays;
+  return MPE_OK;
+}
+
+static int finish_step(mpe_ctx* c, int n, mpe_result* results) {
+  if (!results) return MPE_OK;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(results, c->h_results, (size_t)n * sizeof(mpe_result));
+  return MPE_OK;
+}
+
+// One estimateBodyPose step for n_streams independent PoseEstimators (pose_estimator.cpp:62-147) without a host round trip.
+int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch, long long frame_stride, int width, int height,
+                            int n_streams, const double* times, mpe_result* results) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!frames_device || !times || n_streams < 1) return MPE_E_INVALID;
+  if (n_streams > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "streams or image larger than the context capacity");
+  if (c->cam.nD < 5) return fail(c, MPE_E_UNSUPPORTED, "LEDDetector::distortPoints reads five distortion coefficients (led_detector.cpp:190-194)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int total = c->frame_map ? c->frame_map_total : n_streams;
+  FrameSource src{frames_device, pitch, frame_stride, width, height, total};
+  rc = run_streams_step(c, src, n_streams, times, results != nullptr);
+  if (rc != MPE_OK) return rc;
+  return finish_step(c, n_streams, results);
+}
+
+// Host-image variant: the per-image call of a camera driver (MPENode::imageCallback -> estimateBodyPose,
+// monocular_pose_estimator.cpp:133-159).  Image s (HOST memory, pitch bytes per row) belongs to stream s.
+int mpe_streams_step(mpe_ctx* c, const uint8_t* frames, int pitch, long long frame_stride, int width, int height, int n_streams,
+                     const double* times, mpe_result* results) {
+  int rc = check_configured(c, true);
+  if (rc != MPE_OK) return rc;
+  if (!frames || !times || !results || n_streams < 1 || pitch < width) return MPE_E_INVALID;
+  if (n_streams > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "streams or image larger than the context capacity");
+  if (c->cam.nD < 5) return fail(c, MPE_E_UNSUPPORTED, "LEDDetector::distortPoints reads five distortion coefficients (led_detector.cpp:190-194)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const long long dev_stride = (long long)c->pitch * c->max_h;
+  if (pitch == c->pitch && frame_stride == dev_stride) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->d.frames, frames, (size_t)n_streams * dev_stride, cudaMemcpyHostToDevice, st));
+  } else if (frame_stride == (long long)pitch * height && c->max_h == height) {
+    CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames, c->pitch, frames, pitch, width, (size_t)n_streams * height, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = 0; f < n_streams; ++f)
+      CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames + (size_t)f * dev_stride, c->pitch, frames + (size_t)f * frame_stride, pitch, width, height,
+                                    cudaMemcpyHostToDevice, st));
+  }
+  const int* saved_map = c->frame_map;
+  const int saved_total = c->frame_map_total;
+  c->frame_map = nullptr; c->frame_map_total = 0;          // host images are one per stream
+  FrameSource src{c->d.frames, c->pitch, dev_stride, width, height, n_streams};
+  rc = run_streams_step(c, src, n_streams, times, true);
+  c->frame_map = saved_map; c->frame_map_total = saved_total;
+  if (rc != MPE_OK) return rc;
+  return finish_step(c, n_streams, results);
+}
+
+int mpe_set_graph_replay(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->use_graphs = on != 0; return MPE_OK; }
 
 int mpe_enable_kernel_timing(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->timing = on != 0; return MPE_OK; }
 

@@ -169,6 +169,20 @@ class Context:
         self.check(self.L.mpe_streams_step_device(self.h, C.c_void_p(dev_ptr), pitch, frame_stride, width, height, n, _dp(t), res))
         return res
 
+    def streams_step(self, frames: np.ndarray, times, out=None):
+        """One estimateBodyPose step for len(times) streams from HOST images (S,H,W) uint8 (image s -> stream s): the per-image
+        call of a camera driver.  Returns the ctypes MpeResult array (pass `out` to reuse one)."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        t = np.ascontiguousarray(times, np.float64)
+        n, H, W = frames.shape
+        assert len(t) == n
+        res = out if out is not None else (MpeResult * n)()
+        self.check(self.L.mpe_streams_step(self.h, C.c_void_p(frames.ctypes.data), frames.strides[1], frames.strides[0], W, H, n, _dp(t), res))
+        return res
+
+    def set_graph_replay(self, on: bool):
+        self.check(self.L.mpe_set_graph_replay(self.h, 1 if on else 0))
+
     def copy_poses_device(self, dst_device_ptr: int, n: int):
         self.check(self.L.mpe_copy_poses_device(self.h, n, C.c_void_p(dst_device_ptr)))
 

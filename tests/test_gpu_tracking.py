@@ -89,3 +89,71 @@ def test_streams_with_frame_map_replay(gpu_ctx_752):
             assert a["updated"] == b["updated"] and np.array_equal(a["pose"], b["pose"]) and tuple(a["roi"]) == tuple(b["roi"])
     ctx.streams_set_frame_map(0, 0)
     assert res["updated"].sum() == S
+
+
+def _edited_streams(T):
+    streams = [synth.make_stream_scene(T, n_leds=5, seed=300 + s) for s in range(4)]
+    streams[1].frames[9][:] = 0                      # LEDs vanish: ROI search and the whole-image retry fail
+    streams[1].frames[10][:] = 0
+    other = synth.make_stream_scene(T, n_leds=5, seed=999)
+    for t in range(12, T):                           # spliced trajectory: NN check fails -> brute-force re-initialisation
+        streams[3].frames[t] = other.frames[t]
+    return streams
+
+
+def test_host_step_single_camera_graph_replay_matches_oracle(gpu_ctx_752):
+    """mpe_streams_step with ONE host image per call — the drop-in estimateBodyPose of a camera driver — replayed as a CUDA
+    graph from the third frame on, equals the oracle frame by frame (including the retry / re-initialisation ladders)."""
+    T = 22
+    ctx = gpu_ctx_752
+    for sc in (_edited_streams(T)[1], _edited_streams(T)[3], _edited_streams(T)[0]):
+        ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
+        ctx.streams_reset(1)
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        l0 = ctx.launch_count()
+        n_upd = 0
+        for t in range(T):
+            r = results_to_arrays(ctx.streams_step(sc.frames[t][None], [sc.times[t]]))[0]
+            upd = est.estimate_body_pose(sc.frames[t], sc.times[t])
+            tag = f"frame {t}"
+            assert bool(r["updated"]) == upd, tag
+            assert tuple(r["roi"]) == tuple(est.region_of_interest), tag
+            if upd:
+                n_upd += 1
+                k = r["n_corr"]
+                assert np.array_equal(r["corr"][:2 * k].reshape(k, 2), est.correspondences()), tag
+                dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+                assert dt < 1e-6 and dr < 1e-6, (tag, dt, dr)
+                assert r["gn_iters"] == est.gn_iterations(), tag
+        assert n_upd >= T - 4
+        assert ctx.launch_count() - l0 >= 20 * T      # every step, replayed or not, accounts for its kernel launches
+
+
+def test_host_step_equals_device_step_and_follows_reconfiguration(gpu_ctx_752):
+    """Host-image steps (graph replay) and device-buffer steps (plain launches) give bit-identical records; a configuration
+    change between two steps invalidates the captured graph."""
+    import torch
+    T = 14
+    streams = _edited_streams(T)
+    S = len(streams)
+    sc0 = streams[0]
+    ctx = gpu_ctx_752
+    dev_out = _run(streams, ctx, torch)
+    ctx.streams_reset(S)
+    for t in range(T):
+        frames = np.stack([streams[s].frames[t] for s in range(S)])
+        res = results_to_arrays(ctx.streams_step(frames, [streams[s].times[t] for s in range(S)]))
+        assert res.tobytes() == dev_out[t].tobytes(), f"frame {t}"
+    # reconfigure: threshold 255 -> nothing detected -> no update; the stale graph must not be replayed
+    import dataclasses
+    p = sc0.params
+    p255 = dataclasses.replace(p, threshold_value=255)
+    ctx.set_params(p255)
+    frames = np.stack([streams[s].frames[T - 1] for s in range(S)])
+    res = results_to_arrays(ctx.streams_step(frames, [streams[s].times[T - 1] + 1 / 60 for s in range(S)]))
+    assert res["updated"].sum() == 0 and res["n_det"].sum() == 0
+    ctx.set_params(p)
+    ctx.set_graph_replay(False)
+    res = results_to_arrays(ctx.streams_step(frames, [streams[s].times[T - 1] + 2 / 60 for s in range(S)]))
+    ctx.set_graph_replay(True)
+    assert res["n_det"].min() >= 4
