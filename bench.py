@@ -236,13 +236,67 @@ def run_tracking(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     res = results_to_arrays(ctx.fetch_results(S))
+    launches = ctx.launch_count() - l0
+
+    # ---- e2e: the same streams fed from a PINNED HOST ring (zero-copy ingest): the findLeds kernels read their ROI tiles in place
+    # over PCIe, every step ends with the D2H copy of all result records and a synchronise (wall clock and CUDA events, the larger)
+    e2e = None
+    if not args.no_e2e:
+        host_buf = torch.from_numpy(np.stack([f for sc in seqs for f in sc.frames])).pin_memory()
+        ctx.streams_reset(S)
+        t = 0
+        def hstep(t):
+            fmap.copy_(base + t)
+            return ctx.streams_step_device(host_buf.data_ptr(), W, W * H, W, H, times[t], fetch=True)
+        for _ in range(8 + args.warmup):
+            hstep(t); t += 1
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = hstep(t); t += 1
+        h1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = max((time.perf_counter() - w0) * 1e3, h0.elapsed_time(h1)) / args.steps
+        rr = results_to_arrays(r)
+        # bytes that cross PCIe per step: whole TMA boxes of the tiles each ROI touches (32-row strips + 2R halo rows, 256-px column
+        # tiles + halo and 16-byte alignment) — an estimate from the ROI table, not a counter
+        R = 2
+        box_bytes = ((((256 + 2 * R - 1 + 15) // 4 + 1) + 3) // 4 * 4) * 4 * (32 + 2 * R)
+        tiles = np.ceil(rr["roi"][:, 3] / 32.0) * np.ceil(rr["roi"][:, 2] / 256.0)
+        e2e = {"value": S / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(tiles.sum() * box_bytes), "h2d_bytes_note": "estimated: TMA boxes of the ROI tiles read in place from pinned host memory",
+               "roi_bytes_per_step": int((rr["roi"][:, 2] * rr["roi"][:, 3]).sum()), "whole_image_bytes_per_step": S * W * H,
+               "d2h_bytes_per_step": S * C.sizeof(mpe.MpeResult), "streams_updated_last_step": int(rr["updated"].sum()),
+               "api": "mpe_streams_step_device on the device alias of a pinned host ring (zero-copy ingest) + result records D2H every step"}
     line = {"metric": f"frames/sec ({W}x{H}, {args.leds} LEDs, tracking mode, device-resident streams)", "value": S / (ms * 1e-3), "unit": "frames/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 + f64", "data": "synthetic",
             "config": {"workload": f"{S} streams ({Sd} distinct trajectories replayed), one frame per stream per step, ROI search + NN correspondences + checkCorrespondences + optimisePose",
                        "streams_updated_last_step": int(res["updated"].sum()), "mean_roi_pixels": float(np.mean(res["roi"][:, 2] * res["roi"][:, 3])),
                        "reinitialised_last_step": int(np.sum((res["flags"] & 8) != 0))},
-            "gpu_launches": ctx.launch_count() - l0}
+            "e2e": e2e, "gpu_launches": launches}
+    if not args.no_cpu:
+        # CPU oracle in tracking mode, one thread, on one of the trajectories
+        import cv2
+        cv2.setNumThreads(1)
+        from oracle import pose_oracle
+        n_cpu = 1500
+        sc = synth.make_stream_scene(n_cpu, n_leds=args.leds, width=W, height=H, seed=args.seed + 5)     # one long continuous trajectory
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        for tt_ in range(8):
+            est.estimate_body_pose(sc.frames[tt_], sc.times[tt_])
+        t0c = time.perf_counter()
+        n = 0
+        for tt_ in range(8, n_cpu):
+            est.estimate_body_pose(sc.frames[tt_], sc.times[tt_])
+            n += 1
+            if time.perf_counter() - t0c > 12:
+                break
+        dtc = time.perf_counter() - t0c
+        line["cpu_baseline"] = {"value": n / dtc, "unit": "frames/s", "cores": 1, "kind": "port",
+                                "sample": f"{n} tracking-mode frames in {dtc:.1f} s, one thread (cv2 4.13 findLeds on the ROI + C++ oracle)"}
     print(json.dumps(line), flush=True)
     ctx.close()
 

@@ -170,8 +170,9 @@ int mpe_copy_poses_device(mpe_ctx* ctx, int n_frames, double* poses_device);
  * (current/previous/predicted pose, times, it_since_initialized_).  One call advances every stream by
  * one frame exactly as estimateBodyPose does (predictWithROI, ROI findLeds, findCorrespondences,
  * checkCorrespondences, fall back to initialise, whole-image retry; pose_estimator.cpp:97-144).
- * frames_device: one frame per stream; times: HOST array of n_streams time stamps; results: HOST array or NULL (then
- * fetch them later with mpe_fetch_results). */
+ * frames_device: one frame per stream, any DEVICE-ACCESSIBLE memory — device memory, or page-locked host memory passed by
+ * its device alias (zero-copy: the kernels then read only the ROI tiles over PCIe); times: HOST array of n_streams time
+ * stamps; results: HOST array or NULL (then fetch them later with mpe_fetch_results). */
 int mpe_streams_reset(mpe_ctx* ctx, int n_streams);
 /* Optional indirection for the next mpe_streams_step_device calls: stream s reads image frame_index_device[s] of the buffer
  * (a DEVICE array of n_streams ints; NULL = stream s reads image s).  n_frames_in_buffer = images addressable from the
@@ -189,6 +190,19 @@ int mpe_streams_step_device(mpe_ctx* ctx, const uint8_t* frames_device, int pitc
 int mpe_streams_step(mpe_ctx* ctx, const uint8_t* frames, int pitch, long long frame_stride, int width, int height,
                      int n_streams, const double* times, mpe_result* results);
 int mpe_set_graph_replay(mpe_ctx* ctx, int on);
+
+/* Image ingest of mpe_streams_step (the step BEFORE the hot path: cv_bridge::toCvCopy + the image hand-over of
+ * MPENode::imageCallback, monocular_pose_estimator.cpp:143-159).
+ *   MPE_INGEST_COPY       every image is copied to the GPU in full (one bulk H2D copy), then searched;
+ *   MPE_INGEST_ZERO_COPY  the images must be page-locked (cudaHostAlloc / cudaHostRegister; 16-byte aligned, pitch and
+ *                         frame stride multiples of 16): the findLeds kernels read their ROI tiles in place over PCIe
+ *                         (TMA from host memory), so in tracking mode only ~1/7 of the image bytes leave the host;
+ *   MPE_INGEST_AUTO       (default) zero copy when the images qualify and every stream is tracking, bulk copy otherwise
+ *                         (whole-image searches are cheaper through one copy).
+ * Graph replay needs a stable image address (e.g. one slot of a pinned ring). */
+enum { MPE_INGEST_COPY = 0, MPE_INGEST_ZERO_COPY = 1, MPE_INGEST_AUTO = 2 };
+int mpe_set_ingest_mode(mpe_ctx* ctx, int mode);
+int mpe_get_ingest_stats(const mpe_ctx* ctx, long long* copy_steps, long long* zero_copy_steps, long long* h2d_bytes_copied);
 
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* When enabled, the batch entry points bracket each kernel with CUDA events on the launching stream.

@@ -7,8 +7,11 @@
 //
 // Mapping: one THREAD per P3P problem (the whole solve + the four scorings are straight-line scalar FP64
 // code, so a warp per problem would idle 31 lanes; with thousands of frames per launch there is no shortage
-// of parallelism).  Votes are integer atomics on the frame's global histogram (order-independent, hence exact);
-// bearings come from a tiny prologue kernel, the histogram is decoded by a one-thread-per-frame epilogue kernel.
+// of parallelism).  Votes are integer atomics on the frame's global histogram (order-independent, hence exact).
+// What does not depend on the pairing is hoisted: the LED-triple geometry into a table built by mpe_set_markers, the
+// detection-triple geometry into a per-frame table written by a prologue kernel; hypotheses pass a conservative reject
+// filter and only the survivors are scored with the reference's exact arithmetic.  The histogram is decoded by a
+// one-thread-per-frame epilogue kernel.
 //
 // FP64 / latency bound, not HBM bound: it reads < 1 KB per frame.  Compiled with -fmad=false.
 #include "mpe_internal.cuh"
@@ -17,6 +20,9 @@
 
 namespace mpe {
 
+#ifndef MPE_K2_ROLL_K
+#define MPE_K2_ROLL_K 0     // 1: keep the four back-substitutions rolled (smaller code); measured slower
+#endif
 #ifndef MPE_K2_THREADS
 #define MPE_K2_THREADS 256
 #endif
@@ -46,39 +52,100 @@ __device__ __forceinline__ void unrank_comb3(int n, int idx, int& a, int& b, int
 }
 
 // row j of Combinations::permutationsNoReplacement(n,3) (combinations.cpp:127-244), 0-based:
-// block j/6 = lexicographic combination (a<b<c); rows [c b a],[c a b],[b c a],[b a c],[a b c],[a c b]
+// block j/6 = lexicographic combination (a<b<c); rows [c b a],[c a b],[b c a],[b a c],[a b c],[a c b].
+// Branch-free (lanes of a warp hold different rows): the row pattern is a packed table of positions in (a,b,c).
+__device__ __forceinline__ int pick3(int i, int a, int b, int c) { return i == 0 ? a : (i == 1 ? b : c); }
+__device__ __forceinline__ void unrank_perm3(int n, int j, int& p0, int& p1, int& p2, int& a, int& b, int& c) {
+  unrank_comb3(n, j / 6, a, b, c);
+  const int r6 = j % 6;
+  // six rows x three positions x two bits (p0 lowest): (2,1,0) (2,0,1) (1,2,0) (1,0,2) (0,1,2) (0,2,1) -> 0x06 0x12 0x09 0x21 0x24 0x18
+  const uint32_t e = (uint32_t)(0x624849486ull >> (6 * r6)) & 63u;
+  p0 = pick3(e & 3, a, b, c); p1 = pick3((e >> 2) & 3, a, b, c); p2 = pick3((e >> 4) & 3, a, b, c);
+}
 __device__ __forceinline__ void unrank_perm3(int n, int j, int& p0, int& p1, int& p2) {
   int a, b, c;
-  unrank_comb3(n, j / 6, a, b, c);
-  switch (j % 6) {
-    case 0: p0 = c; p1 = b; p2 = a; break;
-    case 1: p0 = c; p1 = a; p2 = b; break;
-    case 2: p0 = b; p1 = c; p2 = a; break;
-    case 3: p0 = b; p1 = a; p2 = c; break;
-    case 4: p0 = a; p1 = b; p2 = c; break;
-    default: p0 = a; p1 = c; p2 = b; break;
-  }
+  unrank_perm3(n, j, p0, p1, p2, a, b, c);
+}
+
+// m-th (0-based) index of {0,1,2,...} that is none of a < b < c — the same for every lane's trip count, so loops over the
+// unused LEDs / detections stay convergent although each lane excludes a different triple
+__device__ __forceinline__ int nth_unused(int m, int a, int b, int c) {
+  m += (m >= a);
+  m += (m >= b);
+  m += (m >= c);
+  return m;
 }
 
 // PoseEstimator::calculateImageVectors (pose_estimator.cpp:288-301)
-__device__ __forceinline__ void bearing_vector(const DevCamera& cam, double u, double v, double out[3]) {
+__device__ __forceinline__ v3 bearing_vector(const DevCamera& cam, double u, double v) {
   double x = (u - cam.K[2]) / cam.K[0];
   double y = (v - cam.K[5]) / cam.K[4];
   double z = 1;
   double n = sqrt(x * x + y * y + z * z);
-  out[0] = x / n; out[1] = y / n; out[2] = z / n;
+  return v_make(x / n, y / n, z / n);
 }
 
-// setImagePoints -> image_vectors_: one thread per (frame, detection)
-__global__ void bearings_kernel(const K2Args a) {
+// ---- hoisted tables -------------------------------------------------------------------------------------------------
+// (1) LED-triple table, rebuilt by mpe_set_markers: for every row j of permutationsNoReplacement(n_obj,3) the part of
+//     computePoses that depends on the ordered world-point triple only (P3PWorld).  SoA: field-major [kTripleFields][n_perm],
+//     so that lanes with consecutive j load consecutive words.  Field 15 = code: 0 colinear (p3p.cpp:77-80), 1 usable,
+//     2 usable and well conditioned (the conservative reject filter may be applied).
+// (2) detection-triple table, rebuilt every frame by the prologue: for every 3-subset of the detections the bearings-only
+//     part (P3PCamera).  AoS [frame][combo][kComboFields]: the lanes of a warp mostly share the combo (broadcast loads).
+//     Field 12 = code: bit 0 swap (p3p.cpp:101-121), bit 1 well conditioned.
+constexpr double kCondMin = 1e-6;        // sine of the angle that defines a frame; below it the filter is not trusted
+
+__global__ void marker_triples_kernel(const DevPoseParams pp, int n_perm, double* __restrict__ tab) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_perm) return;
+  int o0, o1, o2;
+  unrank_perm3(pp.n_obj, j, o0, o1, o2);
+  const double* mk = pp.markers;
+  P3PWorld W;
+  p3p_world_frame(v_make(mk[3 * o0], mk[3 * o0 + 1], mk[3 * o0 + 2]), v_make(mk[3 * o1], mk[3 * o1 + 1], mk[3 * o1 + 2]),
+                  v_make(mk[3 * o2], mk[3 * o2 + 1], mk[3 * o2 + 2]), W);
+  const double f[kTripleFields] = {W.n1.x, W.n1.y, W.n1.z, W.n2.x, W.n2.y, W.n2.z, W.n3.x, W.n3.y, W.n3.z, W.P1.x, W.P1.y, W.P1.z,
+                                   W.p_1, W.p_2, W.d_12, 0.0};
+  for (int k = 0; k < kTripleFields - 1; ++k) tab[(size_t)k * n_perm + j] = f[k];
+  double code = 0.0;
+  if (!(W.cross_norm == 0.0)) {
+    const double len13 = sqrt(W.p_1 * W.p_1 + W.p_2 * W.p_2);        // |P3 - P1| (P3 has no z component in the world frame)
+    code = (W.cross_norm > kCondMin * W.d_12 * len13) ? 2.0 : 1.0;
+  }
+  tab[(size_t)(kTripleFields - 1) * n_perm + j] = code;
+}
+
+cudaError_t launch_marker_triples(const DevPoseParams& pp, double* table, cudaStream_t st) {
+  const int n = pp.n_obj;
+  const int n_perm = n * (n - 1) * (n - 2);
+  if (n_perm <= 0) return cudaSuccess;
+  marker_triples_kernel<<<(n_perm + 127) / 128, 128, 0, st>>>(pp, n_perm, table);
+  return cudaGetLastError();
+}
+
+// setImagePoints -> image_vectors_ (pose_estimator.cpp:166-170, 288-301) and the bearings-only part of every P3P problem of
+// the frame: kComboLanes threads per frame, each walking over the frame's 3-subsets of the detections
+constexpr int kComboLanes = 32;
+__global__ void combo_setup_kernel(const K2Args a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = i / MPE_MAX_DET, d = i - f * MPE_MAX_DET;
+  const int f = i / kComboLanes, lane = i - f * kComboLanes;
   if (f >= a.n_frames) return;
   if (a.active && !a.active[f]) return;
   const int n_det = a.n_det[f];
-  if (d >= n_det || n_det > MPE_MAX_DET) return;
+  if (n_det < 4 || n_det > MPE_MAX_DET) return;
+  const int n_comb = n_det * (n_det - 1) * (n_det - 2) / 6;
   const double* det = a.det + (size_t)f * a.det_stride * 2;
-  bearing_vector(a.cam, det[2 * d], det[2 * d + 1], a.bearings + ((size_t)f * MPE_MAX_DET + d) * 3);
+  for (int ci = lane; ci < n_comb; ci += kComboLanes) {
+    int d0, d1, d2;
+    unrank_comb3(n_det, ci, d0, d1, d2);
+    P3PCamera Cm;
+    p3p_camera_frame(bearing_vector(a.cam, det[2 * d0], det[2 * d0 + 1]), bearing_vector(a.cam, det[2 * d1], det[2 * d1 + 1]),
+                     bearing_vector(a.cam, det[2 * d2], det[2 * d2 + 1]), Cm);
+    double* o = a.combos + ((size_t)f * kMaxCombos + ci) * kComboFields;
+    o[0] = Cm.e1.x; o[1] = Cm.e1.y; o[2] = Cm.e1.z; o[3] = Cm.e2.x; o[4] = Cm.e2.y; o[5] = Cm.e2.z;
+    o[6] = Cm.e3.x; o[7] = Cm.e3.y; o[8] = Cm.e3.z; o[9] = Cm.f_1; o[10] = Cm.f_2; o[11] = Cm.b;
+    o[12] = (double)(Cm.swap | ((Cm.sin12 > kCondMin) ? 2 : 0));
+  }
 }
 
 // PoseEstimator::correspondencesFromHistogram (pose_estimator.cpp:344-370) on hist (row = detection,
@@ -103,24 +170,130 @@ __device__ int decode_histogram(uint32_t* hist, int n_det, int n_obj, uint32_t t
   return n;
 }
 
-// The sweep.  A CTA walks over the frames blockIdx.x, blockIdx.x + gridDim.x, ... and treats their P3P problems as ONE flat
-// sequence dealt round-robin to its threads (`rot` carries the position over from frame to frame), so no thread waits for a
-// partially filled last iteration and there is no block barrier at all: votes go straight to the global histogram with
-// integer atomics (about a hundred per frame).  (The first version kept a shared-memory histogram per CTA and synchronised
-// twice per frame; 29 % of its warp stalls were barrier waits, 600 problems over 256 threads leave a 35 %-filled third pass.)
+// Exact scoring of one finite pose hypothesis H = [R|C] (camera -> world), exactly as PoseEstimator::initialise does it
+// (pose_estimator.cpp:656-697): general inverse, project2d of the unused LEDs, nearest back-projection for every unused
+// detection, votes.  ids packs d0,d1,d2,o0,o1,o2 (4 bits each).  Not inlined: it runs for ~1 % of the hypotheses.
+__device__ __noinline__ void score_and_vote(const double H[12], uint32_t ids, int n_det, int n_obj, const double* __restrict__ det,
+                                            const double* __restrict__ mk, const double* __restrict__ K, double tol_sq_max,
+                                            uint32_t* __restrict__ ghist) {
+  const int d0 = ids & 15, d1 = (ids >> 4) & 15, d2 = (ids >> 8) & 15;
+  const int o0 = (ids >> 12) & 15, o1 = (ids >> 16) & 15, o2 = (ids >> 20) & 15;
+  const int n_unused_obj = n_obj - 3;
+  double Hi[12], KT[12];
+  h_inverse(H, Hi);                                    // :660
+  kt_product(K, Hi, KT);
+  // sorted copy of the LED triple (the exclusion list of the loops below)
+  int oa = min(o0, min(o1, o2)), oc = max(o0, max(o1, o2)), ob = o0 + o1 + o2 - oa - oc;
+  // back-project the unused LEDs (:658-661), in LED order
+  double bu[MPE_MAX_LEDS - 3], bv[MPE_MAX_LEDS - 3];
+  for (int m = 0; m < n_unused_obj; ++m) {
+    const int ll = nth_unused(m, oa, ob, oc);
+    kt_project(KT, mk[3 * ll], mk[3 * ll + 1], mk[3 * ll + 2], bu[m], bv[m]);
+  }
+  // nearest back-projection for every unused detection (:664, calculateMinDistancesAndPairs :862-906)
+  uint32_t within = 0;            // bit i: unused detection i is within tolerance
+  unsigned long long pairs = 0;   // 4 bits per unused detection: index of the nearest unused LED
+  const int n_unused_det = n_det - 3;
+  for (int ui = 0; ui < n_unused_det; ++ui) {
+    const int kk = nth_unused(ui, d0, d1, d2);
+    const double du = det[2 * kk], dv = det[2 * kk + 1];
+    double best = HUGE_VAL;
+    int bj = 0;
+    for (int j = 0; j < n_unused_obj; ++j) {
+      double dx = du - bu[j], dy = dv - bv[j];
+      double d2v = dx * dx + dy * dy;
+      if (d2v < best) { best = d2v; bj = j; }
+    }
+    if (best <= tol_sq_max) within |= 1u << ui;        // :671  sqrt(best) < tol, see DevPoseParams::back_proj_sq_max
+    pairs |= (unsigned long long)bj << (4 * ui);
+  }
+  if (within) {                                         // :676
+    atomicAdd(&ghist[d0 * n_obj + o0], 1u);             // :680-685
+    atomicAdd(&ghist[d1 * n_obj + o1], 1u);
+    atomicAdd(&ghist[d2 * n_obj + o2], 1u);
+    for (int ui = 0; ui < n_unused_det; ++ui) {         // :687-695
+      if (within & (1u << ui)) {
+        const int kk = nth_unused(ui, d0, d1, d2);
+        const int obj = nth_unused((int)((pairs >> (4 * ui)) & 0xf), oa, ob, oc);   // bj-th unused LED -> LED index
+        atomicAdd(&ghist[kk * n_obj + obj], 1u);
+      }
+    }
+  }
+}
+
+// Conservative reject test: false only if NO unused detection can lie within the back-projection tolerance of ANY unused
+// LED under this hypothesis, so that skipping the exact evaluation cannot change a vote.  It projects with the rigid inverse
+// R^T (X - C) instead of the general 4x4 inverse and compares without dividing:  |K x_c - (u,v,1) z|^2 <= r^2 z^2  with
+// r = tolerance + margin.  H is a product of three frames that are orthonormal to ~1e-10 when both conditioning codes are
+// set, so the two projections differ by < 4e-6 * fx pixels for |z| >= 1e-3 |x_c|_1 (closer to the camera plane, or any NaN,
+// the test answers "maybe"); the host disables the filter unless that is far below the margin.
+// `bb` = centre and half extent of the bounding box of ALL detections of the frame (uc, vc, hu, hv): with many unused detections
+// a projection outside the box grown by r skips its pair loop (kBBox: compiled in only for objects with >= 7 LEDs, where the pair
+// loop is long; for few LEDs the box would only cost registers).
+template <bool kBBox>
+__device__ __forceinline__ bool maybe_within(const double H[12], int oa, int ob, int oc, int d0, int d1, int d2, int n_det, int n_obj,
+                                             const double* __restrict__ det, const double* __restrict__ mk, const double* __restrict__ K,
+                                             double r, const double bb[4]) {
+  bool maybe = false;
+  const int nu_obj = n_obj - 3, nu_det = n_det - 3;
+  const double r2 = r * r;
+  for (int m = 0; m < nu_obj; ++m) {
+    const int ll = nth_unused(m, oa, ob, oc);            // oa < ob < oc: the LED triple of this problem, sorted
+    const double dx = mk[3 * ll] - H[3], dy = mk[3 * ll + 1] - H[7], dz = mk[3 * ll + 2] - H[11];
+    const double xc = H[0] * dx + H[4] * dy + H[8] * dz;
+    const double yc = H[1] * dx + H[5] * dy + H[9] * dz;
+    const double zc = H[2] * dx + H[6] * dy + H[10] * dz;
+    const double au = K[0] * xc + K[1] * yc + K[2] * zc;
+    const double av = K[3] * xc + K[4] * yc + K[5] * zc;
+    const double az = K[6] * xc + K[7] * yc + K[8] * zc;
+    const bool near_plane = !(fabs(az) >= 1e-3 * (fabs(xc) + fabs(yc) + fabs(zc)));
+    maybe = maybe || near_plane;
+    if (kBBox) {
+      const double aaz = fabs(az);
+      const bool outside = fabs(au - bb[0] * az) > (bb[2] + r) * aaz || fabs(av - bb[1] * az) > (bb[3] + r) * aaz;
+      if (outside && !near_plane) continue;              // cannot be within r of any detection
+    }
+    const double lim = r2 * (az * az);
+    for (int i = 0; i < nu_det; ++i) {
+      const int kk = nth_unused(i, d0, d1, d2);          // d0 < d1 < d2 (a combination)
+      const double eu = au - det[2 * kk] * az, ev = av - det[2 * kk + 1] * az;
+      maybe = maybe || !(eu * eu + ev * ev > lim);
+    }
+  }
+  return maybe;
+}
+
+// The sweep.  A CTA walks over the units (frame, part) blockIdx.x, blockIdx.x + gridDim.x, ... (by default exactly one) and
+// treats the unit's P3P problems as one flat sequence dealt round-robin to its threads (`rot` carries the position over from
+// unit to unit).  Per problem: two table look-ups (detection triple, LED triple), the quartic, four back-substitutions; each
+// finite hypothesis goes through the reject filter, and the few survivors are parked in a shared-memory queue that the CTA
+// drains with the exact scoring after a barrier (every kK2DrainEvery passes and at the end of the unit) — so the expensive,
+// rarely needed path runs compacted instead of diverging in most warps.  Votes are integer atomics on the frame's global
+// histogram (order independent).  The block size is chosen at launch so that the unit's last pass is well filled.
+constexpr int kK2DrainEvery = 4;
+
+template <bool kBBox>
 __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel(const K2Args a) {
   const int tid = threadIdx.x;
+  const int n_thr = blockDim.x;
   const int n_obj = a.pp.n_obj;
   const int n_perm = n_obj * (n_obj - 1) * (n_obj - 2);
-  const int n_unused_obj = n_obj - 3;
   const double tol_sq_max = a.pp.back_proj_sq_max;
-  // marker coordinates in shared memory: lanes of a warp index them with different permutations, which the constant
-  // bank (kernel parameters) would serialise
+  // marker coordinates and K in shared memory: lanes of a warp index the markers with different permutations, which the
+  // constant bank (kernel parameters) would serialise
   __shared__ double mk[3 * MPE_MAX_LEDS];
+  __shared__ double Ks[9];
+  __shared__ double q_h[12][kK2Queue];                  // parked hypotheses: H, field-major
+  __shared__ uint32_t q_ids[kK2Queue];
+  __shared__ int q_n[2];
   if (tid < 3 * MPE_MAX_LEDS) mk[tid] = a.pp.markers[tid];
-  __syncthreads();                                       // the only barrier of the kernel
+  if (tid < 9) Ks[tid] = a.cam.K[tid];
+  if (tid < 2) q_n[tid] = 0;
+  __syncthreads();
+  const double* __restrict__ tt = a.triples;
   const int n_units = a.n_frames * a.split;
   int rot = 0;                                          // flat position (mod blockDim) where this unit's first problem falls
+  int par = 0;                                          // which of the two queue counters is being filled
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int f = unit / a.split, part = unit - f * a.split;
     if (a.active && !a.active[f]) continue;
@@ -132,80 +305,81 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
     const int t_begin = part * chunk, t_end = min(total, t_begin + chunk);
     const int count = max(t_end - t_begin, 0);
     const double* det = a.det + (size_t)f * a.det_stride * 2;
-    const double* bear = a.bearings + (size_t)f * MPE_MAX_DET * 3;
+    const double* combos = a.combos + (size_t)f * kMaxCombos * kComboFields;
     uint32_t* ghist = a.hist + (size_t)f * MPE_MAX_DET * MPE_MAX_LEDS;
+    double bb[4] = {0, 0, 0, 0};
+    if (kBBox) {                                        // bounding box of the detections
+      double u0 = det[0], u1 = det[0], v0 = det[1], v1 = det[1];
+      for (int i = 1; i < n_det; ++i) { u0 = fmin(u0, det[2 * i]); u1 = fmax(u1, det[2 * i]); v0 = fmin(v0, det[2 * i + 1]); v1 = fmax(v1, det[2 * i + 1]); }
+      bb[0] = 0.5 * (u0 + u1); bb[1] = 0.5 * (v0 + v1);
+      bb[2] = 0.5 * (u1 - u0) * (1.0 + 1e-12) + 1e-9; bb[3] = 0.5 * (v1 - v0) * (1.0 + 1e-12) + 1e-9;   // rounding of centre / half extent
+    }
 
     int first = tid - rot;
-    if (first < 0) first += kK2Threads;
-    for (int t = t_begin + first; t < t_end; t += kK2Threads) {
-      const int ci = t / n_perm, pj = t - ci * n_perm;
-      int d0, d1, d2, o0, o1, o2;
-      unrank_comb3(n_det, ci, d0, d1, d2);
-      unrank_perm3(n_obj, pj, o0, o1, o2);
+    if (first < 0) first += n_thr;
+    const int n_pass = (count + n_thr - 1) / n_thr;       // uniform over the CTA; a thread's problems are first, first + n_thr, ...
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int t = t_begin + first + pass * n_thr;
+      if (t < t_end) {
+        const int ci = t / n_perm, pj = t - ci * n_perm;
+        if (tt[(size_t)15 * n_perm + pj] != 0.0) {          // else: colinear LED triple (tested on the unswapped order, p3p.cpp:77-80)
+          const double* cb = combos + (size_t)ci * kComboFields;
+          const int ccode = (int)cb[12];
+          // the exchange of points 1 and 2 selects the table row of the exchanged triple: within a block of six rows
+          // [c b a],[c a b],[b c a],[b a c],[a b c],[a c b] the partner rows are 0<->2, 1<->5, 3<->4
+          int tj = pj;
+          if (ccode & 1) { const int r6 = pj % 6; tj = pj - r6 + ((0x134052 >> (4 * r6)) & 7); }
+          const bool filt = a.use_filter && (ccode & 2) && tt[(size_t)15 * n_perm + tj] == 2.0;
+          P3PSetup S;
+          S.e1 = v_make(cb[0], cb[1], cb[2]); S.e2 = v_make(cb[3], cb[4], cb[5]); S.e3 = v_make(cb[6], cb[7], cb[8]);
+          S.f_1 = cb[9]; S.f_2 = cb[10]; S.b = cb[11];
+          S.n1 = v_make(tt[tj], tt[(size_t)n_perm + tj], tt[(size_t)2 * n_perm + tj]);
+          S.n2 = v_make(tt[(size_t)3 * n_perm + tj], tt[(size_t)4 * n_perm + tj], tt[(size_t)5 * n_perm + tj]);
+          S.n3 = v_make(tt[(size_t)6 * n_perm + tj], tt[(size_t)7 * n_perm + tj], tt[(size_t)8 * n_perm + tj]);
+          S.P1 = v_make(tt[(size_t)9 * n_perm + tj], tt[(size_t)10 * n_perm + tj], tt[(size_t)11 * n_perm + tj]);
+          S.p_1 = tt[(size_t)12 * n_perm + tj]; S.p_2 = tt[(size_t)13 * n_perm + tj]; S.d_12 = tt[(size_t)14 * n_perm + tj];
+          p3p_quartic(S.f_1, S.f_2, S.p_1, S.p_2, S.d_12, S.b, S.roots);
 
-      P3PSetup S;
-      int rc = p3p_setup(v_make(bear[3 * d0], bear[3 * d0 + 1], bear[3 * d0 + 2]), v_make(bear[3 * d1], bear[3 * d1 + 1], bear[3 * d1 + 2]),
-                         v_make(bear[3 * d2], bear[3 * d2 + 1], bear[3 * d2 + 2]), v_make(mk[3 * o0], mk[3 * o0 + 1], mk[3 * o0 + 2]),
-                         v_make(mk[3 * o1], mk[3 * o1 + 1], mk[3 * o1 + 2]), v_make(mk[3 * o2], mk[3 * o2 + 1], mk[3 * o2 + 2]), S);
-      if (rc != 0) continue;
+          int d0, d1, d2, o0, o1, o2, oa, ob, oc;
+          unrank_comb3(n_det, ci, d0, d1, d2);
+          unrank_perm3(n_obj, pj, o0, o1, o2, oa, ob, oc);
+          const uint32_t ids = (uint32_t)d0 | ((uint32_t)d1 << 4) | ((uint32_t)d2 << 8) | ((uint32_t)o0 << 12) | ((uint32_t)o1 << 16) | ((uint32_t)o2 << 20);
 
-      for (int k = 0; k < 4; ++k) {
-        double H[12];
-        if (!p3p_solution(S, k, H)) continue;
-        if (!h_is_finite(H)) continue;                       // pose_estimator.cpp:653
-        double Hi[12], KT[12];
-        h_inverse(H, Hi);                                    // :660
-        kt_product(a.cam.K, Hi, KT);
-        // back-project the unused LEDs (:658-661)
-        double bu[MPE_MAX_LEDS - 3], bv[MPE_MAX_LEDS - 3];
-        int m = 0;
-        for (int ll = 0; ll < n_obj; ++ll) {
-          if (ll == o0 || ll == o1 || ll == o2) continue;
-          kt_project(KT, mk[3 * ll], mk[3 * ll + 1], mk[3 * ll + 2], bu[m], bv[m]);
-          ++m;
-        }
-        // nearest back-projection for every unused detection (:664, calculateMinDistancesAndPairs :862-906)
-        uint32_t within = 0;            // bit i: unused detection i is within tolerance
-        unsigned long long pairs = 0;   // 4 bits per unused detection: index of the nearest unused LED
-        int ui = 0;
-        for (int kk = 0; kk < n_det; ++kk) {
-          if (kk == d0 || kk == d1 || kk == d2) continue;
-          const double du = det[2 * kk], dv = det[2 * kk + 1];
-          double best = HUGE_VAL;
-          int bj = 0;
-          for (int j = 0; j < n_unused_obj; ++j) {
-            double dx = du - bu[j], dy = dv - bv[j];
-            double d2v = dx * dx + dy * dy;
-            if (d2v < best) { best = d2v; bj = j; }
-          }
-          if (best <= tol_sq_max) within |= 1u << ui;        // :671  sqrt(best) < tol, see DevPoseParams::back_proj_sq_max
-          pairs |= (unsigned long long)bj << (4 * ui);
-          ++ui;
-        }
-        if (within) {                                         // :676
-          atomicAdd(&ghist[d0 * n_obj + o0], 1u);             // :680-685
-          atomicAdd(&ghist[d1 * n_obj + o1], 1u);
-          atomicAdd(&ghist[d2 * n_obj + o2], 1u);
-          ui = 0;
-          for (int kk = 0; kk < n_det; ++kk) {                // :687-695
-            if (kk == d0 || kk == d1 || kk == d2) continue;
-            if (within & (1u << ui)) {
-              int bj = (int)((pairs >> (4 * ui)) & 0xf);
-              int obj = -1, cnt = 0;                          // bj-th unused LED -> LED index
-              for (int ll = 0; ll < n_obj; ++ll) {
-                if (ll == o0 || ll == o1 || ll == o2) continue;
-                if (cnt == bj) { obj = ll; break; }
-                ++cnt;
-              }
-              atomicAdd(&ghist[kk * n_obj + obj], 1u);
+#if MPE_K2_ROLL_K
+#pragma unroll 1
+#endif
+          for (int k = 0; k < 4; ++k) {
+            double H[12];
+            if (!p3p_solution(S, k, H)) continue;
+            if (!h_is_finite(H)) continue;                       // pose_estimator.cpp:653
+            if (filt && !maybe_within<kBBox>(H, oa, ob, oc, d0, d1, d2, n_det, n_obj, det, mk, Ks, a.filter_r, bb)) continue;
+            const int slot = atomicAdd(&q_n[par], 1);
+            if (slot < kK2Queue) {
+#pragma unroll
+              for (int e = 0; e < 12; ++e) q_h[e][slot] = H[e];
+              q_ids[slot] = ids;
+            } else {
+              score_and_vote(H, ids, n_det, n_obj, det, mk, Ks, tol_sq_max, ghist);   // queue full: score in place
             }
-            ++ui;
           }
         }
       }
+      const bool last = (pass + 1 == n_pass);
+      if (last || (pass % kK2DrainEvery) == kK2DrainEvery - 1) {
+        __syncthreads();                                  // every survivor so far is parked
+        const int n_q = min(q_n[par], kK2Queue);
+        if (tid == 0) q_n[par ^ 1] = 0;
+        for (int e = tid; e < n_q; e += n_thr) {
+          double H[12];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) H[i] = q_h[i][e];
+          score_and_vote(H, q_ids[e], n_det, n_obj, det, mk, Ks, tol_sq_max, ghist);
+        }
+        par ^= 1;
+        if (!last || unit + (int)gridDim.x < n_units) __syncthreads();   // the queue storage is reused
+      }
     }
-    rot = (rot + count) % kK2Threads;
-    __syncwarp();                                       // reconverge the warp before the next frame (lanes ran 2 or 3 problems)
+    rot = (rot + count) % n_thr;
   }
 }
 
@@ -231,17 +405,30 @@ __global__ void decode_kernel(const K2Args a) {
 }
 
 cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st) {
-  bearings_kernel<<<(a.n_frames * MPE_MAX_DET + 255) / 256, 256, 0, st>>>(a);
+  combo_setup_kernel<<<(int)(((size_t)a.n_frames * kComboLanes + 255) / 256), 256, 0, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int n_units = a.n_frames * a.split;
-  static int mult = -1;
+  static int mult = -1, forced_bs = -1;
   if (mult < 0) { const char* e = getenv("MPE_K2_GRID_MULT"); mult = e ? atoi(e) : 0; }
+  if (forced_bs < 0) { const char* e = getenv("MPE_K2_THREADS"); forced_bs = e ? atoi(e) : 0; }
   // default: one CTA per (frame, part) — measured faster than fewer persistent CTAs (hardware CTA scheduling balances the
-  // tail; 8192 frames: 2.07 ms against 2.31 ms with 4 CTAs per resident slot); MPE_K2_GRID_MULT overrides for experiments
+  // tail); MPE_K2_GRID_MULT overrides for experiments
   int grid = (mult == 0) ? n_units : n_sms * MPE_K2_MINBLOCKS * mult;
   if (grid > n_units) grid = n_units;
-  p3p_sweep_kernel<<<grid, kK2Threads, 0, st>>>(a);
+  // block size: 256 threads (measured best for 600 and 18 816 problems per frame: the kernel is latency bound, a fuller last
+  // pass with 160 threads and five CTAs per SM was 3 % slower); units with fewer problems than that get a CTA of their size
+  int bs = kK2Threads;
+  {
+    const int n = a.pp.n_obj;
+    const long long total = (long long)n * (n - 1) * (n - 2) / 6 * n * (n - 1) * (n - 2);
+    const long long per_unit = (total + a.split - 1) / a.split;
+    if (per_unit < kK2Threads) bs = (int)((per_unit + 31) / 32 * 32);
+    if (bs < 64) bs = 64;
+    if (forced_bs >= 32 && forced_bs <= kK2Threads && forced_bs % 32 == 0) bs = forced_bs;
+  }
+  if (a.pp.n_obj >= 7) p3p_sweep_kernel<true><<<grid, bs, 0, st>>>(a);
+  else p3p_sweep_kernel<false><<<grid, bs, 0, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   decode_kernel<<<(a.n_frames + 127) / 128, 128, 0, st>>>(a);

@@ -3,6 +3,7 @@
 // k1_find_leds.cu / k2_p3p_sweep.cu / k3_validate_refine.cu.  There is no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -30,7 +31,8 @@ struct DevBuffers {
   double* det = nullptr;           // [max_batch][MPE_MAX_BLOBS][2]
   float* centers = nullptr;        // [max_batch][MPE_MAX_BLOBS][2]
   uint32_t* hist = nullptr;        // [max_batch][MPE_MAX_DET*MPE_MAX_LEDS]
-  double* bearings = nullptr;      // [max_batch][MPE_MAX_DET][3]
+  double* combos = nullptr;        // [max_batch][kMaxCombos][kComboFields]  K2 detection-triple table
+  double* triples = nullptr;       // [kTripleFields][kMaxPerms]             K2 LED-triple table (rebuilt by mpe_set_markers)
   uint32_t* corr = nullptr;        // [max_batch][2*MPE_MAX_LEDS]
   int* n_corr = nullptr;           // [max_batch]
   double* pose = nullptr;          // [max_batch][16]
@@ -81,6 +83,7 @@ struct mpe_ctx {
   int frame_map_total = 0;
   std::vector<cudaEvent_t> chunk_events;
   // CUDA-graph replay of the tracking step (mpe_streams_step*): the ~30 small launches of one step become one graph launch
+  bool k2_filter = true;                  // K2 conservative reject filter (MPE_K2_NO_FILTER=1 scores every hypothesis exactly)
   bool use_graphs = true;
   unsigned long long cfg_version = 0;     // bumped by every configuration call; a stale graph is rebuilt
   struct StepGraphKey {
@@ -94,6 +97,11 @@ struct mpe_ctx {
   StepGraphKey graph_key{}, pending_key{};   // a key is run eagerly once (function attributes get configured), captured on its second use
   bool have_pending = false;
   cudaGraphExec_t graph_exec = nullptr;
+  // image ingest of the host-image tracking step (mpe_streams_step)
+  int ingest_mode = MPE_INGEST_AUTO;
+  std::vector<uint8_t> stream_tracking;   // host mirror: stream s has produced a pose since the last reset (it_since_initialized_ >= 1)
+  int n_tracking = 0;
+  long long h2d_bytes_copied = 0, zero_copy_steps = 0, copy_steps = 0;
   long long graph_launches = 0;           // kernel launches contained in one replay
   long long graph_replays = 0;
 };
@@ -300,7 +308,17 @@ int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* acti
   k.pp = c->pp;
   k.split = choose_split(c, n);
   k.hist = c->d.hist + (size_t)slot0 * MPE_MAX_DET * MPE_MAX_LEDS;
-  k.bearings = c->d.bearings + (size_t)slot0 * MPE_MAX_DET * 3;
+  k.combos = c->d.combos + (size_t)slot0 * kMaxCombos * kComboFields;
+  k.triples = c->d.triples;
+  // conservative reject filter (k2_p3p_sweep.cu: maybe_within): radius = tolerance + margin; trusted only while its error bound
+  // 4e-6 * fx pixels is far below the margin
+  {
+    const double tol = c->pp.back_projection_pixel_tolerance;
+    const double fmax_ = std::fmax(std::fabs(c->cam.K[0]), std::fabs(c->cam.K[4]));
+    const double margin = 0.25;
+    k.use_filter = (c->k2_filter && std::isfinite(tol) && tol > 0 && std::isfinite(fmax_) && 4e-6 * fmax_ * 8 <= margin) ? 1 : 0;
+    k.filter_r = tol + margin;
+  }
   k.corr = c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS;
   k.n_corr = c->d.n_corr + slot0;
   k.frame_flags = c->d.flags + slot0;
@@ -439,7 +457,9 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.det, B * MPE_MAX_BLOBS * 2));
   CREATE_TRY(dev_alloc(&c->d.centers, B * MPE_MAX_BLOBS * 2));
   CREATE_TRY(dev_alloc(&c->d.hist, B * MPE_MAX_DET * MPE_MAX_LEDS));
-  CREATE_TRY(dev_alloc(&c->d.bearings, B * MPE_MAX_DET * 3));
+  CREATE_TRY(dev_alloc(&c->d.combos, B * kMaxCombos * kComboFields));
+  CREATE_TRY(dev_alloc(&c->d.triples, (size_t)kTripleFields * kMaxPerms));
+  { const char* e = getenv("MPE_K2_NO_FILTER"); c->k2_filter = !(e && e[0] == '1'); }
   CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.n_corr, B));
   CREATE_TRY(dev_alloc(&c->d.pose, B * 16));
@@ -487,7 +507,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
-  cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.bearings); cudaFree(c->d.corr);
+  cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.combos); cudaFree(c->d.triples); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
   cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
   cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);
@@ -525,6 +545,11 @@ int mpe_set_markers(mpe_ctx* c, const double* xyz, int n) {
   c->pp.n_obj = n;
   for (int i = 0; i < 3 * n; ++i) c->pp.markers[i] = xyz[i];
   c->pp.histogram_threshold = (n >= 3) ? num_combinations_ref((unsigned)n, 3u) : 0u;   // pose_estimator.cpp:54
+  // LED-triple table of the K2 sweep (world frame of every ordered marker triple), computed on the device with the kernels' arithmetic
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, launch_marker_triples(c->pp, c->d.triples, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  ++c->launches;
   c->have_markers = true;
   ++c->cfg_version;
   return MPE_OK;
@@ -784,6 +809,8 @@ int mpe_streams_reset(mpe_ctx* c, int n_streams) {
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, launch_track_reset(c->d.streams, n_streams, c->stream));
   ++c->launches;
+  c->stream_tracking.assign(c->max_batch, 0);
+  c->n_tracking = 0;
   return MPE_OK;
 }
 
@@ -884,7 +911,19 @@ static int finish_step(mpe_ctx* c, int n, mpe_result* results) {
   if (!results) return MPE_OK;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   std::memcpy(results, c->h_results, (size_t)n * sizeof(mpe_result));
+  // host mirror of "this stream is tracking" (it_since_initialized_ never returns to 0, pose_estimator.cpp:806-809)
+  if ((int)c->stream_tracking.size() < c->max_batch) c->stream_tracking.assign(c->max_batch, 0);
+  for (int i = 0; i < n; ++i)
+    if (results[i].updated && !c->stream_tracking[i]) { c->stream_tracking[i] = 1; ++c->n_tracking; }
   return MPE_OK;
+}
+
+// Is `p` page-locked host memory the GPU can read in place (cudaHostAlloc / cudaHostRegister)?  Returns its device alias.
+static const uint8_t* device_alias_of_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return (const uint8_t*)at.devicePointer;
 }
 
 // One estimateBodyPose step for n_streams independent PoseEstimators (pose_estimator.cpp:62-147) without a host round trip.
@@ -915,23 +954,56 @@ int mpe_streams_step(mpe_ctx* c, const uint8_t* frames, int pitch, long long fra
   CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const long long dev_stride = (long long)c->pitch * c->max_h;
-  if (pitch == c->pitch && frame_stride == dev_stride) {
-    CUDA_TRY(c, cudaMemcpyAsync(c->d.frames, frames, (size_t)n_streams * dev_stride, cudaMemcpyHostToDevice, st));
-  } else if (frame_stride == (long long)pitch * height && c->max_h == height) {
-    CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames, c->pitch, frames, pitch, width, (size_t)n_streams * height, cudaMemcpyHostToDevice, st));
-  } else {
-    for (int f = 0; f < n_streams; ++f)
-      CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames + (size_t)f * dev_stride, c->pitch, frames + (size_t)f * frame_stride, pitch, width, height,
-                                    cudaMemcpyHostToDevice, st));
+  // ---- ingest: copy the whole images, or let the kernels read the ROI tiles in place over PCIe (zero copy)
+  const uint8_t* alias = nullptr;
+  if (c->ingest_mode != MPE_INGEST_COPY && (pitch % 16) == 0 && (frame_stride % 16) == 0) {
+    alias = device_alias_of_pinned(frames);
+    if (alias && ((uintptr_t)alias & 15)) alias = nullptr;
   }
+  if (c->ingest_mode == MPE_INGEST_ZERO_COPY && !alias)
+    return fail(c, MPE_E_INVALID, "zero-copy ingest needs page-locked images (cudaHostAlloc / cudaHostRegister), 16-byte aligned, pitch and frame stride multiples of 16");
+  // AUTO: in place only when every stream is tracking (ROI search: ~1/7 of the image bytes); whole-image searches are
+  // cheaper through one bulk copy (53 GB/s against ~24 GB/s for tile reads over PCIe)
+  const bool zero_copy = alias && (c->ingest_mode == MPE_INGEST_ZERO_COPY || c->n_tracking >= n_streams);
   const int* saved_map = c->frame_map;
   const int saved_total = c->frame_map_total;
   c->frame_map = nullptr; c->frame_map_total = 0;          // host images are one per stream
-  FrameSource src{c->d.frames, c->pitch, dev_stride, width, height, n_streams};
-  rc = run_streams_step(c, src, n_streams, times, true);
+  if (zero_copy) {
+    ++c->zero_copy_steps;
+    FrameSource src{alias, pitch, frame_stride, width, height, n_streams};
+    rc = run_streams_step(c, src, n_streams, times, true);
+  } else {
+    ++c->copy_steps;
+    c->h2d_bytes_copied += (long long)n_streams * width * height;
+    if (pitch == c->pitch && frame_stride == dev_stride) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->d.frames, frames, (size_t)n_streams * dev_stride, cudaMemcpyHostToDevice, st));
+    } else if (frame_stride == (long long)pitch * height && c->max_h == height) {
+      CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames, c->pitch, frames, pitch, width, (size_t)n_streams * height, cudaMemcpyHostToDevice, st));
+    } else {
+      for (int f = 0; f < n_streams; ++f)
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->d.frames + (size_t)f * dev_stride, c->pitch, frames + (size_t)f * frame_stride, pitch, width, height,
+                                      cudaMemcpyHostToDevice, st));
+    }
+    FrameSource src{c->d.frames, c->pitch, dev_stride, width, height, n_streams};
+    rc = run_streams_step(c, src, n_streams, times, true);
+  }
   c->frame_map = saved_map; c->frame_map_total = saved_total;
   if (rc != MPE_OK) return rc;
   return finish_step(c, n_streams, results);
+}
+
+int mpe_set_ingest_mode(mpe_ctx* c, int mode) {
+  if (!c || mode < MPE_INGEST_COPY || mode > MPE_INGEST_AUTO) return MPE_E_INVALID;
+  c->ingest_mode = mode;
+  return MPE_OK;
+}
+
+int mpe_get_ingest_stats(const mpe_ctx* c, long long* copy_steps, long long* zero_copy_steps, long long* h2d_bytes_copied) {
+  if (!c) return MPE_E_INVALID;
+  if (copy_steps) *copy_steps = c->copy_steps;
+  if (zero_copy_steps) *zero_copy_steps = c->zero_copy_steps;
+  if (h2d_bytes_copied) *h2d_bytes_copied = c->h2d_bytes_copied;
+  return MPE_OK;
 }
 
 int mpe_set_graph_replay(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->use_graphs = on != 0; return MPE_OK; }

@@ -14,6 +14,11 @@ constexpr int kMaxTaps = 2 * kMaxRadius + 1;
 constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
 constexpr int kK1Threads = 256;
 constexpr int kCandCap = 256;        // candidate contour starts buffered per frame-warp in K1b
+constexpr int kMaxCombos = MPE_MAX_DET * (MPE_MAX_DET - 1) * (MPE_MAX_DET - 2) / 6;   // 3-subsets of the detections (560)
+constexpr int kMaxPerms = MPE_MAX_LEDS * (MPE_MAX_LEDS - 1) * (MPE_MAX_LEDS - 2);     // ordered LED triples (3360)
+constexpr int kComboFields = 13;     // K2 detection-triple record (doubles)
+constexpr int kTripleFields = 16;    // K2 LED-triple table fields (doubles)
+constexpr int kK2Queue = 192;        // hypotheses a K2 CTA can park for exact scoring before it scores in place
 
 // Camera model as the kernels consume it.
 struct DevCamera {
@@ -96,7 +101,10 @@ struct K2Args {
   DevPoseParams pp;
   int split;                 // CTAs per frame
   uint32_t* hist;            // [n_frames][MPE_MAX_DET*MPE_MAX_LEDS], zeroed before launch
-  double* bearings;          // [n_frames][MPE_MAX_DET][3] image_vectors_ (written by the prologue kernel)
+  double* combos;            // [n_frames][kMaxCombos][kComboFields] bearings-only part of every detection triple (prologue kernel)
+  const double* triples;     // [kTripleFields][n_perm] LED-triple table (mpe_set_markers)
+  double filter_r;           // back-projection tolerance + margin: radius of the conservative reject filter
+  int use_filter;
   uint32_t* corr;            // [n_frames][2*MPE_MAX_LEDS]
   int* n_corr;               // [n_frames]
   int* frame_flags;          // [n_frames] in/out
@@ -160,6 +168,7 @@ cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radi
 cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);
 cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st);
+cudaError_t launch_marker_triples(const DevPoseParams& pp, double* table, cudaStream_t st);
 cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st);
 cudaError_t launch_p3p_batch(const double* f, const double* P, int n, double* sol, int* status, cudaStream_t st);
 size_t find_leds_smem_bytes(const K1Geom& g, int radius, int stages);

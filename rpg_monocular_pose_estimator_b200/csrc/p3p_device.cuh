@@ -191,47 +191,76 @@ struct P3PSetup {
 // rows-as-vectors matrix * vector
 __device__ __forceinline__ v3 rows_mul(v3 r0, v3 r1, v3 r2, v3 v) { return v_make(v_dot(r0, v), v_dot(r1, v), v_dot(r2, v)); }
 
-// returns 0, or -1 if the world points are colinear (p3p.cpp:77-80)
-__device__ __forceinline__ int p3p_setup(v3 f1, v3 f2, v3 f3in, v3 P1, v3 P2, v3 P3, P3PSetup& S) {
-  v3 temp1 = v_sub(P2, P1), temp2 = v_sub(P3, P1);
-  if (v_norm(v_cross(temp1, temp2)) == 0.0) return -1;
+// ---- computePoses up to the quartic, in three parts so that callers can hoist what does not change between problems.
+// The arithmetic (operations and their order) is that of p3p.cpp:65-190 in every composition below.
 
-  v3 e1 = f1;
-  v3 e3 = v_cross(f1, f2);
-  e3 = v_divs(e3, v_norm(e3));
-  v3 e2 = v_cross(e3, e1);
-  v3 f3 = rows_mul(e1, e2, e3, f3in);
-  if (f3.z > 0.0) {   // p3p.cpp:101-121: swap the roles of points 1 and 2
-    v3 t = f1; f1 = f2; f2 = t;
-    e1 = f1;
-    e3 = v_cross(f1, f2);
-    e3 = v_divs(e3, v_norm(e3));
-    e2 = v_cross(e3, e1);
-    f3 = rows_mul(e1, e2, e3, f3in);
-    t = P1; P1 = P2; P2 = t;
-  }
+// Part W — everything that depends on the ordered world-point triple only (p3p.cpp:74-80, 124-141): the colinearity
+// test, the world frame N = [n1 n2 n3]^T, P3 in that frame (p_1, p_2) and d_12.
+struct P3PWorld {
+  v3 n1, n2, n3, P1;
+  double p_1, p_2, d_12;
+  double cross_norm;      // |(P2-P1) x (P3-P1)|: 0 -> colinear (the reference's reject test)
+};
+__device__ __forceinline__ void p3p_world_frame(v3 P1, v3 P2, v3 P3, P3PWorld& W) {
+  v3 temp1 = v_sub(P2, P1), temp2 = v_sub(P3, P1);
+  W.cross_norm = v_norm(v_cross(temp1, temp2));
   v3 n1 = v_sub(P2, P1);
   n1 = v_divs(n1, v_norm(n1));
   v3 n3 = v_cross(n1, v_sub(P3, P1));
   n3 = v_divs(n3, v_norm(n3));
   v3 n2 = v_cross(n3, n1);
   v3 P3n = rows_mul(n1, n2, n3, v_sub(P3, P1));
+  W.n1 = n1; W.n2 = n2; W.n3 = n3; W.P1 = P1;
+  W.p_1 = P3n.x; W.p_2 = P3n.y;
+  W.d_12 = v_norm(v_sub(P2, P1));
+}
 
-  double d_12 = v_norm(v_sub(P2, P1));
-  double f_1 = f3.x / f3.z;
-  double f_2 = f3.y / f3.z;
-  double p_1 = P3n.x;
-  double p_2 = P3n.y;
+// Part C — everything that depends on the three bearing vectors only (p3p.cpp:88-121, 142-154): the camera frame
+// T = [e1 e2 e3]^T after the possible exchange of points 1 and 2, f_1, f_2 and b.  swap != 0: the caller must exchange
+// world points 1 and 2 (p3p.cpp:117-119).
+struct P3PCamera {
+  v3 e1, e2, e3;
+  double f_1, f_2, b;
+  double sin12;           // |f1 x f2| (conditioning of the frame; not part of the reference's arithmetic)
+  int swap;
+};
+__device__ __forceinline__ void p3p_camera_frame(v3 f1, v3 f2, v3 f3in, P3PCamera& Cm) {
+  v3 e1 = f1;
+  v3 e3 = v_cross(f1, f2);
+  double nn = v_norm(e3);
+  e3 = v_divs(e3, nn);
+  v3 e2 = v_cross(e3, e1);
+  v3 f3 = rows_mul(e1, e2, e3, f3in);
+  int swap = 0;
+  if (f3.z > 0.0) {   // p3p.cpp:101-121: swap the roles of points 1 and 2
+    v3 t = f1; f1 = f2; f2 = t;
+    e1 = f1;
+    e3 = v_cross(f1, f2);
+    nn = v_norm(e3);
+    e3 = v_divs(e3, nn);
+    e2 = v_cross(e3, e1);
+    f3 = rows_mul(e1, e2, e3, f3in);
+    swap = 1;
+  }
   double cos_beta = v_dot(f1, f2);
   double b = 1 / (1 - cos_beta * cos_beta) - 1;
   b = (cos_beta < 0) ? -sqrt(b) : sqrt(b);
+  Cm.e1 = e1; Cm.e2 = e2; Cm.e3 = e3;
+  Cm.f_1 = f3.x / f3.z;
+  Cm.f_2 = f3.y / f3.z;
+  Cm.b = b;
+  Cm.sin12 = nn;
+  Cm.swap = swap;
+}
 
+// Part Q — quartic coefficients (p3p.cpp:171-185, same association) and its roots.
+__device__ __forceinline__ void p3p_quartic(double f_1, double f_2, double p_1, double p_2, double d_12, double b, double roots[4]) {
   double f_1_pw2 = f_1 * f_1, f_2_pw2 = f_2 * f_2;
   double p_1_pw2 = p_1 * p_1, p_1_pw3 = p_1_pw2 * p_1, p_1_pw4 = p_1_pw3 * p_1;
   double p_2_pw2 = p_2 * p_2, p_2_pw3 = p_2_pw2 * p_2, p_2_pw4 = p_2_pw3 * p_2;
   double d_12_pw2 = d_12 * d_12, b_pw2 = b * b;
 
-  double factors[5];   // p3p.cpp:171-185, same association
+  double factors[5];
   factors[0] = -f_2_pw2 * p_2_pw4 - p_2_pw4 * f_1_pw2 - p_2_pw4;
   factors[1] = 2 * p_2_pw3 * d_12 * b + 2 * f_2_pw2 * p_2_pw3 * d_12 * b - 2 * f_2 * p_2_pw3 * f_1 * d_12;
   factors[2] = -f_2_pw2 * p_2_pw2 * p_1_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2
@@ -243,10 +272,24 @@ __device__ __forceinline__ int p3p_setup(v3 f1, v3 f2, v3 f3in, v3 P1, v3 P2, v3
   factors[4] = -2 * f_2 * p_2_pw2 * f_1 * p_1 * d_12 * b + f_2_pw2 * p_2_pw2 * d_12_pw2 + 2 * p_1_pw3 * d_12
       - p_1_pw2 * d_12_pw2 + f_2_pw2 * p_2_pw2 * p_1_pw2 - p_1_pw4 - 2 * f_2_pw2 * p_2_pw2 * p_1 * d_12
       + p_2_pw2 * f_1_pw2 * p_1_pw2 + f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2;
+  solve_quartic(factors, roots);
+}
 
-  solve_quartic(factors, S.roots);
-  S.e1 = e1; S.e2 = e2; S.e3 = e3; S.n1 = n1; S.n2 = n2; S.n3 = n3; S.P1 = P1;
-  S.f_1 = f_1; S.f_2 = f_2; S.p_1 = p_1; S.p_2 = p_2; S.d_12 = d_12; S.b = b;
+__device__ __forceinline__ void p3p_assemble(const P3PCamera& Cm, const P3PWorld& W, P3PSetup& S) {
+  S.e1 = Cm.e1; S.e2 = Cm.e2; S.e3 = Cm.e3; S.n1 = W.n1; S.n2 = W.n2; S.n3 = W.n3; S.P1 = W.P1;
+  S.f_1 = Cm.f_1; S.f_2 = Cm.f_2; S.p_1 = W.p_1; S.p_2 = W.p_2; S.d_12 = W.d_12; S.b = Cm.b;
+  p3p_quartic(Cm.f_1, Cm.f_2, W.p_1, W.p_2, W.d_12, Cm.b, S.roots);
+}
+
+// The whole thing for one problem.  Returns 0, or -1 if the world points are colinear (p3p.cpp:77-80).
+__device__ __forceinline__ int p3p_setup(v3 f1, v3 f2, v3 f3in, v3 P1, v3 P2, v3 P3, P3PSetup& S) {
+  v3 temp1 = v_sub(P2, P1), temp2 = v_sub(P3, P1);
+  if (v_norm(v_cross(temp1, temp2)) == 0.0) return -1;
+  P3PCamera Cm;
+  p3p_camera_frame(f1, f2, f3in, Cm);
+  P3PWorld W;
+  if (Cm.swap) p3p_world_frame(P2, P1, P3, W); else p3p_world_frame(P1, P2, P3, W);
+  p3p_assemble(Cm, W, S);
   return 0;
 }
 

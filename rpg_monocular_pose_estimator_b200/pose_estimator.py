@@ -180,6 +180,16 @@ class Context:
         self.check(self.L.mpe_streams_step(self.h, C.c_void_p(frames.ctypes.data), frames.strides[1], frames.strides[0], W, H, n, _dp(t), res))
         return res
 
+    INGEST_COPY, INGEST_ZERO_COPY, INGEST_AUTO = 0, 1, 2
+
+    def set_ingest_mode(self, mode: int):
+        self.check(self.L.mpe_set_ingest_mode(self.h, int(mode)))
+
+    def ingest_stats(self):
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self.check(self.L.mpe_get_ingest_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"copy_steps": a.value, "zero_copy_steps": b.value, "h2d_bytes_copied": c.value}
+
     def set_graph_replay(self, on: bool):
         self.check(self.L.mpe_set_graph_replay(self.h, 1 if on else 0))
 

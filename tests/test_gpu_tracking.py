@@ -157,3 +157,44 @@ def test_host_step_equals_device_step_and_follows_reconfiguration(gpu_ctx_752):
     res = results_to_arrays(ctx.streams_step(frames, [streams[s].times[T - 1] + 2 / 60 for s in range(S)]))
     ctx.set_graph_replay(True)
     assert res["n_det"].min() >= 4
+
+
+def test_zero_copy_ingest_reads_pinned_images_in_place(gpu_ctx_752):
+    """mpe_streams_step with page-locked images: AUTO switches from bulk copies to in-place ROI reads (TMA from host memory)
+    once every stream is tracking; the records are bit-identical to the copy mode; ZERO_COPY refuses pageable memory."""
+    import torch
+    from rpg_monocular_pose_estimator_b200 import MpeError
+    T = 10
+    streams = [synth.make_stream_scene(T, n_leds=5, seed=300 + s) for s in range(4)]
+    S = len(streams)
+    sc0 = streams[0]
+    ctx = gpu_ctx_752
+    ctx.set_camera(sc0.K, sc0.D); ctx.set_params(sc0.params); ctx.set_markers(sc0.markers)
+    pinned = torch.from_numpy(np.stack([np.stack([streams[s].frames[t] for s in range(S)]) for t in range(T)])).pin_memory().numpy()
+    times = [[streams[s].times[t] for s in range(S)] for t in range(T)]
+    out = {}
+    for mode in (ctx.INGEST_COPY, ctx.INGEST_AUTO, ctx.INGEST_ZERO_COPY):
+        ctx.set_ingest_mode(mode)
+        ctx.streams_reset(S)
+        st0 = ctx.ingest_stats()
+        out[mode] = [results_to_arrays(ctx.streams_step(pinned[t], times[t])).copy() for t in range(T)]
+        st1 = ctx.ingest_stats()
+        dz, dc = st1["zero_copy_steps"] - st0["zero_copy_steps"], st1["copy_steps"] - st0["copy_steps"]
+        if mode == ctx.INGEST_COPY:
+            assert (dz, dc) == (0, T)
+        elif mode == ctx.INGEST_AUTO:
+            assert dc >= 1 and dz >= T - 3, (dz, dc)           # cold start by copy, tracking in place
+        else:
+            assert (dz, dc) == (T, 0)
+    for t in range(T):
+        assert out[ctx.INGEST_COPY][t].tobytes() == out[ctx.INGEST_AUTO][t].tobytes() == out[ctx.INGEST_ZERO_COPY][t].tobytes(), t
+    assert out[ctx.INGEST_COPY][-1]["updated"].sum() == S
+    # pageable images: AUTO falls back to copying, ZERO_COPY is an error
+    pageable = np.stack([streams[s].frames[0] for s in range(S)])
+    ctx.set_ingest_mode(ctx.INGEST_ZERO_COPY)
+    ctx.streams_reset(S)
+    with pytest.raises(MpeError):
+        ctx.streams_step(pageable, times[0])
+    ctx.set_ingest_mode(ctx.INGEST_AUTO)
+    r = results_to_arrays(ctx.streams_step(pageable, times[0]))
+    assert r["updated"].sum() == S
