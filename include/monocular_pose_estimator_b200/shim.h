@@ -6,9 +6,13 @@
 //   * Without them (this build image has neither) minimal stand-ins with the same member syntax are used, so the shim can
 //     still be compiled and exercised (tests/cpp/shim_demo.cpp); define MPE_SHIM_FORCE_STANDIN to force that mode.
 //
-// The heavy stages are the CUDA kernels behind mpe_find_leds / mpe_initialise / mpe_check_correspondences /
-// mpe_optimise_pose; the state machine (estimateBodyPose, pose_estimator.cpp:62-147) and the tiny sequential helpers of
-// tracking mode (predictPose, determineROI, findCorrespondences) stay on the host exactly as in the reference.
+// PoseEstimator::estimateBodyPose (pose_estimator.cpp:62-147) has two implementations here (setDeviceLoop):
+//   * device loop (default): ONE call per image, mpe_streams_step with a single stream — the whole state machine and the
+//     estimator state live on the GPU (CUDA-graph replay), the members are refreshed from the returned record;
+//   * stage by stage: the state machine and the tiny sequential helpers of tracking mode (predictPose, determineROI,
+//     findCorrespondences) run on the host exactly as in the reference and call one CUDA stage at a time
+//     (mpe_find_leds / mpe_initialise / mpe_check_correspondences / mpe_optimise_pose) — for callers that drive the public
+//     stage methods and setters themselves.
 #ifndef MPE_B200_SHIM_H_
 #define MPE_B200_SHIM_H_
 
@@ -248,11 +252,21 @@ class PoseEstimator {
   double getPredictedTime() { return predicted_time_; }
   unsigned lastGaussNewtonIterations() const { return last_gn_iters_; }
 
+  // Where the per-frame state machine runs.  true (default): one mpe_streams_step call per image — predictWithROI, findLeds,
+  // findCorrespondences / checkCorrespondences / initialise and optimisePose all run on the GPU with the estimator state
+  // resident there (replayed as a single CUDA graph), and the members below are refreshed from the returned record; this is
+  // what MPENode needs (it only calls estimateBodyPose and the getters).  false: the state machine runs here, stage by stage
+  // through mpe_find_leds / mpe_initialise / mpe_check_correspondences / mpe_optimise_pose, so that a caller may interleave
+  // its own calls to the public stage methods and setters (setPredictedPose, setCorrespondences, ...) between frames.
+  void setDeviceLoop(bool on) { device_loop_ = on; }
+  bool deviceLoop() const { return device_loop_; }
+
   // pose_estimator.cpp:62-147
   bool estimateBodyPose(ImageT image, double time_to_predict) {
     pose_updated_ = false;
     ensureContext(image.cols, image.rows);
     push();   // the caller may have changed the public fields since the last frame
+    if (device_loop_) return estimateBodyPoseOnDevice(image, time_to_predict);
     List2DPoints detected;
     if (it_since_initialized_ < 1) {
       setPredictedTime(time_to_predict);
@@ -279,6 +293,36 @@ class PoseEstimator {
           repeat_check = false;
         }
       } while (repeat_check);
+    }
+    return pose_updated_;
+  }
+
+  // estimateBodyPose as one device step (mpe_streams_step with a single stream)
+  bool estimateBodyPoseOnDevice(const ImageT& image, double time_to_predict) {
+    mpe_result r;
+    detail::check(ctx_, mpe_streams_step(ctx_, image.data, (int)(size_t)image.step, (long long)image.step * image.rows, image.cols, image.rows, 1,
+                                         &time_to_predict, &r), "mpe_streams_step");
+    predicted_time_ = time_to_predict;
+    region_of_interest_ = RectT(r.roi.x, r.roi.y, r.roi.width, r.roi.height);
+    const int nd = r.n_det < MPE_MAX_DET ? r.n_det : MPE_MAX_DET;
+    if (nd > 0) {                                                               // pixel_positions untouched when nothing was found (led_detector.cpp:91)
+      distorted_detection_centers_.resize(nd);
+      List2DPoints det; det.resize(nd);
+      for (int i = 0; i < nd; ++i) {
+        det(i)(0) = r.det[2 * i]; det(i)(1) = r.det[2 * i + 1];
+        distorted_detection_centers_[i] = Point2fT(r.centers[2 * i], r.centers[2 * i + 1]);
+      }
+      if (nd >= (int)min_num_leds_detected_) image_points_ = det;
+    }
+    correspondences_.resize(r.n_corr, 2);
+    for (int i = 0; i < r.n_corr; ++i) { correspondences_(i, 0) = r.corr[2 * i]; correspondences_(i, 1) = r.corr[2 * i + 1]; }
+    std::memcpy(predicted_pose_, r.pose, sizeof(r.pose));
+    last_gn_iters_ = (unsigned)r.gn_iters;
+    if (r.updated) {                                                            // optimiseAndUpdatePose bookkeeping (:802-812, :794-800)
+      std::memcpy(cov_, r.cov, sizeof(r.cov));
+      if (it_since_initialized_ < 2) it_since_initialized_++;
+      updatePose();
+      pose_updated_ = true;
     }
     return pose_updated_;
   }
@@ -423,7 +467,7 @@ class PoseEstimator {
     if (ctx_) mpe_destroy(ctx_);
     ctx_ = nullptr; ctx_w_ = w; ctx_h_ = h;
     if (mpe_create(&ctx_, 0, 1, w, h) != MPE_OK) { ctx_ = nullptr; throw std::runtime_error("mpe_create failed: no CUDA device? (there is no CPU fallback)"); }
-    markers_dirty_ = true;
+    markers_dirty_ = true; pushed_valid_ = false;
   }
   void push() {   // the caller writes the public fields directly, so configuration is pushed before every device stage
     if (!ctx_) ensureContext(752, 480);
@@ -433,19 +477,32 @@ class PoseEstimator {
     p.max_circular_distortion = max_circular_distortion_; p.back_projection_pixel_tolerance = back_projection_pixel_tolerance_;
     p.nearest_neighbour_pixel_tolerance = nearest_neighbour_pixel_tolerance_; p.certainty_threshold = certainty_threshold_;
     p.valid_correspondence_threshold = valid_correspondence_threshold_;
-    detail::check(ctx_, mpe_set_params(ctx_, &p), "mpe_set_params");
+    // only what changed is pushed: every configuration call invalidates the captured CUDA graph of the device loop
+    if (!pushed_valid_ || std::memcmp(&p, &pushed_params_, sizeof(p)) != 0) {
+      detail::check(ctx_, mpe_set_params(ctx_, &p), "mpe_set_params");
+      pushed_params_ = p;
+    }
     double K[9]; detail::camera_to_rowmajor(camera_matrix_K_, K);
-    detail::check(ctx_, mpe_set_camera(ctx_, K, camera_distortion_coeffs_.data(), (int)camera_distortion_coeffs_.size()), "mpe_set_camera");
+    if (!pushed_valid_ || std::memcmp(K, pushed_K_, sizeof(K)) != 0 || camera_distortion_coeffs_ != pushed_D_) {
+      detail::check(ctx_, mpe_set_camera(ctx_, K, camera_distortion_coeffs_.data(), (int)camera_distortion_coeffs_.size()), "mpe_set_camera");
+      std::memcpy(pushed_K_, K, sizeof(K)); pushed_D_ = camera_distortion_coeffs_;
+    }
     if (markers_dirty_) {
       std::vector<double> xyz(3 * object_points_.size());
       for (unsigned i = 0; i < object_points_.size(); ++i) for (int k = 0; k < 3; ++k) xyz[3 * i + k] = object_points_(i)(k);
       detail::check(ctx_, mpe_set_markers(ctx_, xyz.data(), (int)object_points_.size()), "mpe_set_markers");
       markers_dirty_ = false;
     }
-    detail::check(ctx_, mpe_set_histogram_threshold(ctx_, histogram_threshold_), "mpe_set_histogram_threshold");
+    if (!pushed_valid_ || histogram_threshold_ != pushed_hist_) {
+      detail::check(ctx_, mpe_set_histogram_threshold(ctx_, histogram_threshold_), "mpe_set_histogram_threshold");
+      pushed_hist_ = histogram_threshold_;
+    }
+    pushed_valid_ = true;
   }
 
   mpe_ctx* ctx_; int ctx_w_, ctx_h_; bool markers_dirty_ = true;
+  bool device_loop_ = true, pushed_valid_ = false;
+  mpe_params pushed_params_; double pushed_K_[9]; std::vector<double> pushed_D_; unsigned pushed_hist_ = 0;
   double current_pose_[16], previous_pose_[16], predicted_pose_[16], cov_[36];   // row-major
   double current_time_, previous_time_, predicted_time_;
   List4DPoints object_points_;

@@ -211,6 +211,10 @@ int mpe_get_ingest_stats(const mpe_ctx* ctx, long long* copy_steps, long long* z
  * [4] blur_tiles (K1c, exact fixed-point blur of the hot tiles). */
 int mpe_enable_kernel_timing(mpe_ctx* ctx, int on);
 int mpe_get_kernel_times(mpe_ctx* ctx, float ms_out[5]);
+/* The brute-force sweep of initialise() rejects most pose hypotheses with a conservative, division-free projection test before
+ * the reference's exact scoring (results are identical by construction).  0 switches the test off, so that
+ * every finite hypothesis goes through the exact arithmetic — for A/B verification. */
+int mpe_set_k2_filter(mpe_ctx* ctx, int on);
 /* number of kernel launches issued by this context so far */
 long long mpe_kernel_launch_count(const mpe_ctx* ctx);
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "mpe_set_histogram_threshold", "mpe_get_histogram_threshold", "mpe_find_leds", "mpe_initialise",
     "mpe_check_correspondences", "mpe_optimise_pose", "mpe_p3p_compute_poses", "mpe_estimate_batch",
     "mpe_estimate_batch_device", "mpe_estimate_batch_device_async", "mpe_fetch_results", "mpe_synchronize", "mpe_copy_poses_device",
-    "mpe_streams_reset", "mpe_streams_set_frame_map", "mpe_streams_step_device", "mpe_streams_step", "mpe_set_graph_replay", "mpe_set_ingest_mode", "mpe_get_ingest_stats",
+    "mpe_streams_reset", "mpe_streams_set_frame_map", "mpe_streams_step_device", "mpe_streams_step", "mpe_set_graph_replay", "mpe_set_ingest_mode", "mpe_get_ingest_stats", "mpe_set_k2_filter",
     "mpe_enable_kernel_timing", "mpe_get_kernel_times",
     "mpe_kernel_launch_count",
 ]
@@ -94,6 +94,7 @@ def load_library():
         "mpe_streams_step": ([vp, vp, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, dp, C.POINTER(MpeResult)], C.c_int),
         "mpe_set_graph_replay": ([vp, C.c_int], C.c_int),
         "mpe_set_ingest_mode": ([vp, C.c_int], C.c_int),
+        "mpe_set_k2_filter": ([vp, C.c_int], C.c_int),
         "mpe_get_ingest_stats": ([vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)], C.c_int),
         "mpe_enable_kernel_timing": ([vp, C.c_int], C.c_int),
         "mpe_get_kernel_times": ([vp, fp], C.c_int),

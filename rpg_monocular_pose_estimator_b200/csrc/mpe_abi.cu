@@ -20,6 +20,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr int kTrackTileWidthPx = 256;   // column-tile width of the tracking-mode K1 launches (ROIs are ~100-200 px wide)
+constexpr int kLanes = 4;                // sub-batches of one cold batch that may be in flight at once (two streams, alternating)
+constexpr int kPipelineMinFrames = 1024; // below this a batch is not split
 constexpr size_t kPoolPerFrame = 1024;   // hot-word pool entries reserved per frame of capacity (overflow degrades to the dense path)
 
 struct DevBuffers {
@@ -45,7 +47,7 @@ struct DevBuffers {
   double* check_sums = nullptr;    // [max_batch][MPE_MAX_LEDS*3]
   uint4* hot_tiles = nullptr;      // [max_batch * flags_per_frame]
   uint16_t* pool = nullptr;        // [max_batch * kPoolPerFrame]
-  uint32_t* counters = nullptr;    // [2]
+  uint32_t* counters = nullptr;    // [kLanes][2]  (one pair per concurrently running sub-batch)
   // tracking loop
   StreamState* streams = nullptr;  // [max_batch]
   Roi* result_rois = nullptr;      // [max_batch]
@@ -64,7 +66,9 @@ struct mpe_ctx {
   int max_batch = 0, max_w = 0, max_h = 0;
   int pitch = 0;                  // device frame pitch (multiple of 16)
   int mask_wpr = 0, flags_per_frame = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pipeline = false;           // split large cold batches over two streams: measured SLOWER (3.06 vs 2.80 ms @8192); MPE_PIPELINE=1 enables
   DevBuffers d;
   mpe_result* h_results = nullptr;   // pinned
   // configuration
@@ -224,7 +228,7 @@ void time_end(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) { cudaEventRe
 
 // K1a + K1b over frames [f0, f0+n) of `src`, outputs into slots [slot0, slot0+n) of the context buffers.
 int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, Roi roi, const Roi* rois_dev, cudaStream_t st,
-                  int forced_tw = 0, const int* frame_map = nullptr, const uint8_t* active = nullptr) {
+                  int forced_tw = 0, const int* frame_map = nullptr, const uint8_t* active = nullptr, int lane = 0) {
   int radius = 0;
   K1aArgs a{};
   if (!gaussian_taps_8u(c->params.gaussian_sigma, &radius, a.taps))
@@ -252,7 +256,7 @@ int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, 
   a.hot_tiles = c->d.hot_tiles + (size_t)slot0 * c->flags_per_frame;
   a.pool = c->d.pool + (size_t)slot0 * kPoolPerFrame;
   a.pool_capacity = (uint32_t)((size_t)n * kPoolPerFrame);
-  a.counters = c->d.counters;
+  a.counters = c->d.counters + 2 * lane;
   a.frames = sub.base;
   a.pitch = src.pitch;
   a.frame_stride = src.frame_stride;
@@ -382,9 +386,9 @@ __global__ void pack_results_kernel(int n, Roi roi, const int* n_det, const int*
 }
 
 // The whole cold path for frames [f0, f0+n) of src -> device results slots [slot0, slot0+n)
-int run_cold(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, cudaStream_t st) {
+int run_cold(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, cudaStream_t st, int lane = 0) {
   Roi full{0, 0, src.width, src.height};                       // pose_estimator.cpp:72
-  int rc = run_find_leds(c, src, f0, n, slot0, full, nullptr, st);
+  int rc = run_find_leds(c, src, f0, n, slot0, full, nullptr, st, 0, nullptr, nullptr, lane);
   if (rc != MPE_OK) return rc;
   rc = run_sweep(c, slot0, n, st, nullptr);                    // setImagePoints + initialise (histogram + decode)
   if (rc != MPE_OK) return rc;
@@ -399,6 +403,29 @@ int run_cold(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, cudaS
                                                        c->d.results + slot0);
   CUDA_TRY(c, cudaGetLastError());
   ++c->launches;
+  return MPE_OK;
+}
+
+// A large cold batch as kLanes sub-batches alternating on two streams: the latency-bound, low-occupancy stages of one
+// sub-batch (contour tracing with a warp per frame, Gauss-Newton with a thread per frame, the sparse blur) overlap the wide
+// stages of the other (the HBM-bound scan, the FP64-bound P3P sweep).  Sub-batches own disjoint slots of every buffer.
+// Per-kernel event timing (mpe_enable_kernel_timing) needs the stages back to back and switches the split off.
+// EXPERIMENT, off by default: on B200 the four sets of kernel ramps and tails cost more than the overlap wins (8192 frames:
+// 3.06 ms split against 2.80 ms back to back; 1080p: 1.71 against 1.35 ms).
+int run_cold_pipelined(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st) {
+  if (!c->pipeline || c->timing || n < kPipelineMinFrames) return run_cold(c, src, 0, n, 0, st);
+  const int per = (n + kLanes - 1) / kLanes;
+  CUDA_TRY(c, cudaEventRecord(c->ev_fork, st));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+  for (int p = 0; p < kLanes; ++p) {
+    const int f0 = p * per;
+    const int np = (n - f0 < per) ? n - f0 : per;
+    if (np <= 0) break;
+    int rc = run_cold(c, src, f0, np, f0, (p & 1) ? c->aux_stream : st, p);
+    if (rc != MPE_OK) return rc;
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev_join, c->aux_stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   return MPE_OK;
 }
 
@@ -447,6 +474,10 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   c->flags_per_frame = ((max_height + kTileRows - 1) / kTileRows) * (n_ct > n_ct_track ? n_ct : n_ct_track);
   CREATE_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CREATE_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  { const char* e = getenv("MPE_PIPELINE"); c->pipeline = (e && e[0] == '1'); }
   c->stream = c->own_stream;
   size_t B = (size_t)max_batch;
   CREATE_TRY(dev_alloc(&c->d.frames, B * c->pitch * max_height));
@@ -473,7 +504,7 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.check_cnt, B * 2));
   CREATE_TRY(dev_alloc(&c->d.hot_tiles, B * c->flags_per_frame));
   CREATE_TRY(dev_alloc(&c->d.pool, B * kPoolPerFrame));
-  CREATE_TRY(dev_alloc(&c->d.counters, 2));
+  CREATE_TRY(dev_alloc(&c->d.counters, 2 * kLanes));
   CREATE_TRY(dev_alloc(&c->d.streams, B));
   CREATE_TRY(dev_alloc(&c->d.result_rois, B));
   CREATE_TRY(dev_alloc(&c->d.pred_px, B * MPE_MAX_LEDS * 2));
@@ -517,6 +548,9 @@ void mpe_destroy(mpe_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
@@ -733,7 +767,7 @@ int mpe_estimate_batch_device_async(mpe_ctx* c, const uint8_t* frames_device, in
   if (n_frames > c->max_batch || width > c->max_w || height > c->max_h) return fail(c, MPE_E_CAPACITY, "batch or image larger than the context capacity");
   CUDA_TRY(c, cudaSetDevice(c->device));
   FrameSource src{frames_device, pitch, frame_stride, width, height, n_frames};
-  return run_cold(c, src, 0, n_frames, 0, c->stream);
+  return run_cold_pipelined(c, src, n_frames, c->stream);
 }
 
 int mpe_fetch_results(mpe_ctx* c, int n_frames, mpe_result* results) {
@@ -1005,6 +1039,8 @@ int mpe_get_ingest_stats(const mpe_ctx* c, long long* copy_steps, long long* zer
   if (h2d_bytes_copied) *h2d_bytes_copied = c->h2d_bytes_copied;
   return MPE_OK;
 }
+
+int mpe_set_k2_filter(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->k2_filter = on != 0; ++c->cfg_version; return MPE_OK; }
 
 int mpe_set_graph_replay(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->use_graphs = on != 0; return MPE_OK; }
 

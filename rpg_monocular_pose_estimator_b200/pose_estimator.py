@@ -190,6 +190,9 @@ class Context:
         self.check(self.L.mpe_get_ingest_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"copy_steps": a.value, "zero_copy_steps": b.value, "h2d_bytes_copied": c.value}
 
+    def set_k2_filter(self, on: bool):
+        self.check(self.L.mpe_set_k2_filter(self.h, 1 if on else 0))
+
     def set_graph_replay(self, on: bool):
         self.check(self.L.mpe_set_graph_replay(self.h, 1 if on else 0))
 

@@ -3,6 +3,7 @@
 // Input: a little binary scene file written by tests/test_gpu_cpp_shim.py.  Output: one text line per frame.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #define MPE_SHIM_FORCE_STANDIN 1
 #include "monocular_pose_estimator_b200/shim.h"
@@ -10,7 +11,8 @@
 using namespace monocular_pose_estimator;
 
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: shim_demo scene.bin\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: shim_demo scene.bin [stage]\n"); return 2; }
+  const bool stage_mode = argc > 2 && std::string(argv[2]) == "stage";   // stage by stage on the host instead of the device loop
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror("open"); return 2; }
   int hdr[4];
@@ -26,6 +28,7 @@ int main(int argc, char** argv) {
 
   try {
     PoseEstimator pe;
+    pe.setDeviceLoop(!stage_mode);
     for (int i = 0; i < 9; ++i) pe.camera_matrix_K_.k[i] = K[i];                 // MPENode::cameraInfoCallback
     pe.camera_distortion_coeffs_.assign(D, D + 5);
     pe.detection_threshold_value_ = (int)params[0];                              // MPENode::dynamicParametersCallback

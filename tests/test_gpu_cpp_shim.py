@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cpp_shim_tracking_sequence(tmp_path):
+@pytest.mark.parametrize("mode", ["device_loop", "stage"])
+def test_cpp_shim_tracking_sequence(tmp_path, mode):
     exe = os.path.join(ROOT, "build", "shim_demo")
     if not os.path.exists(exe):
         subprocess.check_call(["python", "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
@@ -30,7 +31,7 @@ def test_cpp_shim_tracking_sequence(tmp_path):
                           p.max_circular_distortion, p.back_projection_pixel_tolerance, p.nearest_neighbour_pixel_tolerance,
                           p.certainty_threshold, p.valid_correspondence_threshold, p.roi_border_thickness], np.float64).tobytes())
         f.write(np.ascontiguousarray(sc.times, np.float64).tobytes()); f.write(sc.frames.tobytes())
-    out = subprocess.run([exe, str(scene)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, str(scene)] + (["stage"] if mode == "stage" else []), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     lines = [l.split() for l in out.stdout.strip().splitlines()]
     assert len(lines) == len(sc.frames)

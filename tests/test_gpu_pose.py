@@ -163,3 +163,61 @@ def test_too_few_leds_is_not_an_error(gpu_ctx_752):
     assert res[1]["updated"] == 0 and res[1]["n_det"] == 0
     est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
     assert bool(res[0]["updated"]) == est.estimate_body_pose(frames[0], 0.0)
+
+
+def _hist(ctx, det):
+    return ctx.initialise(det)[1]
+
+
+def test_sweep_reject_filter_never_changes_a_vote(gpu_ctx_752):
+    """The K2 sweep drops most hypotheses with a conservative projection test before the reference's exact scoring.  With the
+    test switched off every finite hypothesis takes the exact path, so the two histograms must be IDENTICAL — on real
+    detections, on junk detections (many near-tolerance cases), for tiny and huge tolerances, for a near-colinear LED triple,
+    for detection pairs one pixel apart, and against the oracle on a sample."""
+    import dataclasses
+    ctx = gpu_ctx_752
+    rng = np.random.default_rng(77)
+    K, D = synth.camera()
+    base = synth.Params()
+    n_cases = n_votes = 0
+    try:
+        for n_leds in (4, 5, 6, 8):
+            mk = rng.uniform(-0.15, 0.15, size=(n_leds, 3))
+            if n_leds == 6:                                   # LEDs 0,1,2 almost on a line (conditioning code 1: filter must stand back)
+                mk[2] = mk[0] + 0.6 * (mk[1] - mk[0]) + rng.normal(size=3) * 1e-9
+            for tol in (0.01, 1.0, 5.0, 60.0):
+                p = dataclasses.replace(base, back_projection_pixel_tolerance=tol)
+                ctx.set_camera(K, D); ctx.set_params(p); ctx.set_markers(mk)
+                for rep in range(6 if n_leds < 8 else 2):
+                    # a real view of the object ...
+                    Rm = synth.rodrigues(rng.normal(size=3) * 0.7)
+                    t = np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.15, 0.15), rng.uniform(0.5, 1.2)])
+                    cam = (Rm @ mk.T).T + t
+                    det = np.stack([K[0, 0] * cam[:, 0] / cam[:, 2] + K[0, 2], K[1, 1] * cam[:, 1] / cam[:, 2] + K[1, 2]], axis=1)
+                    det = det + rng.normal(size=det.shape) * 0.3
+                    if rep % 3 == 1:                          # ... or junk: uniformly random detections
+                        det = np.stack([rng.uniform(0, 752, n_leds + 1), rng.uniform(0, 480, n_leds + 1)], axis=1)
+                    if rep % 3 == 2:                          # ... or the view plus a detection one pixel next to another
+                        det = np.vstack([det, det[0] + [1.0, 0.0]])
+                    det = np.ascontiguousarray(det[rng.permutation(len(det))])
+                    ctx.set_k2_filter(True)
+                    h_on = _hist(ctx, det)
+                    ctx.set_k2_filter(False)
+                    h_off = _hist(ctx, det)
+                    assert np.array_equal(h_on, h_off), (n_leds, tol, rep, h_on, h_off)
+                    n_cases += 1; n_votes += int(h_on.sum())
+                    if rep == 0 and tol == 5.0:
+                        est = pose_oracle.PoseEstimatorOracle(K, D, mk, p)
+                        est.set_image_points(det)
+                        est.initialise()
+                        assert np.array_equal(h_on, est.histogram()), (n_leds, h_on, est.histogram())
+        # absurd focal length: the filter's error bound no longer holds a margin, the host must switch it off by itself
+        Kbig = K.copy(); Kbig[0, 0] *= 100; Kbig[1, 1] *= 100
+        ctx.set_camera(Kbig, D); ctx.set_params(base); ctx.set_markers(mk)
+        det = np.stack([rng.uniform(0, 752, 6), rng.uniform(0, 480, 6)], axis=1)
+        ctx.set_k2_filter(True); h_on = _hist(ctx, det)
+        ctx.set_k2_filter(False); h_off = _hist(ctx, det)
+        assert np.array_equal(h_on, h_off)
+    finally:
+        ctx.set_k2_filter(True)
+    assert n_cases >= 70 and n_votes > 1000
