@@ -34,6 +34,18 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT, N_LEDS = 752, 480, 5
 
 
+def load_traffic(batch, width, height):
+    """dram__bytes_read + dram__bytes_write of the scan kernel from the committed `ncu --set full` capture of the same launch
+    shape (profiles/ncu_traffic.json, written by profiles/summarise.py); None when no capture of this shape is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if (d.get("batch"), d.get("width"), d.get("height")) == (batch, width, height):
+            return d["dram_bytes"]
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -317,7 +329,10 @@ def run_latency(args):
     T = 40 + args.steps * 20
     sc = synth.make_stream_scene(T, n_leds=args.leds, width=W, height=H, seed=args.seed)
     out = {}
-    for label, frames in (("pinned", torch.from_numpy(sc.frames).pin_memory().numpy()), ("pageable", sc.frames)):
+    # the camera driver's receive buffer: ONE slot, pinned or pageable, rewritten for every image (a stable address keeps the CUDA
+    # graph of the step valid; pinned + AUTO ingest lets the kernels read the ROI in place once the stream is tracking)
+    slots = {"pinned": torch.empty((H, W), dtype=torch.uint8).pin_memory().numpy(), "pageable": np.empty((H, W), np.uint8)}
+    for label, slot in slots.items():
         for graphs in (True, False):
             ctx = mpe.Context(0, 1, W, H)
             ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
@@ -327,11 +342,12 @@ def run_latency(args):
             tarr = np.zeros(1)
             tp = tarr.ctypes.data_as(C.POINTER(C.c_double))
             L, h = ctx.L, ctx.h
+            ptr = C.c_void_p(slot.ctypes.data)
             lat, upd = [], 0
             l0 = ctx.launch_count()
             for t in range(T):
                 tarr[0] = sc.times[t]
-                ptr = C.c_void_p(frames[t].ctypes.data)
+                slot[:] = sc.frames[t]               # the image arrives (not timed: the reference receives it the same way)
                 t0 = time.perf_counter()
                 rc = L.mpe_streams_step(h, ptr, W, W * H, W, H, 1, tp, res)
                 t1 = time.perf_counter()
@@ -340,9 +356,11 @@ def run_latency(args):
                 if t >= 40:
                     lat.append((t1 - t0) * 1e6)
             lat = np.array(lat)
+            st = ctx.ingest_stats()
             out[f"{label}_{'graph' if graphs else 'launches'}"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
                                                                     "mean_us": float(lat.mean()), "frames_updated": upd, "frames": T,
-                                                                    "gpu_launches_per_frame": (ctx.launch_count() - l0) / T}
+                                                                    "gpu_launches_per_frame": (ctx.launch_count() - l0) / T,
+                                                                    "zero_copy_steps": st["zero_copy_steps"], "copy_steps": st["copy_steps"]}
             ctx.close()
     # cameras per call: n independent streams advanced by ONE mpe_streams_step (host images in, host records out)
     sweep = []
@@ -555,7 +573,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches_timed,
             "roofline": {"kernel": "scan_kernel (K1a: TMA-streamed threshold scan of every ROI byte; findLeds hot loop)", "bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": k1_gbs / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": k1_gbs / peak, "peak_source": peak_src, "traffic": load_traffic(B, W, H),
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kt[0]},
             "dominant_kernel": names[int(np.argmax(kt))],
             "kernel_times_note": "stage times from a separate pass with CUDA events around every stage (sum = %.3f ms)" % ksum,

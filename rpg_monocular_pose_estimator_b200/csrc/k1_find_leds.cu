@@ -500,8 +500,9 @@ __device__ __forceinline__ bool mv_bit(const MaskView& m, int x, int y) {
 }
 
 // direction codes as OpenCV: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE
-__device__ __forceinline__ int dir_dx(int s) { return (s == 0 || s == 1 || s == 7) ? 1 : ((s == 3 || s == 4 || s == 5) ? -1 : 0); }
-__device__ __forceinline__ int dir_dy(int s) { return (s == 1 || s == 2 || s == 3) ? -1 : ((s == 5 || s == 6 || s == 7) ? 1 : 0); }
+// (two bits per direction, value + 1, packed: dx = 1,1,0,-1,-1,-1,0,1 and dy = 0,-1,-1,-1,0,1,1,1)
+__device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
 
 struct Contour {
   long long a00, a10, a01;
@@ -623,8 +624,21 @@ __device__ bool is_enclosed(const MaskView& m, int px, int py) {
     if (!blocked_r) return false;
   }
   {
+    // upwards: only rows whose row flag says "contains foreground" can block (mv_word returns 0 for the others)
     bool blocked_u = false;
-    for (int y = py - 1; y >= 0 && !blocked_u; --y) blocked_u = mv_bit(m, px, y);
+    if (py > 0) {
+      const int wi = px >> 5;
+      const int ct = (m.roi_n_ct == 1) ? 0 : min(wi / m.words_per_ct, m.roi_n_ct - 1);
+      for (int s = (py - 1) >> 5; s >= 0 && !blocked_u; --s) {
+        uint32_t fl = m.flags[s * m.n_ct + ct];
+        if (s == ((py - 1) >> 5)) fl &= 0xffffffffu >> (31 - ((py - 1) & 31));     // rows of this strip above py
+        while (fl && !blocked_u) {
+          const int r = 31 - __clz(fl);
+          fl &= ~(1u << r);
+          blocked_u = mv_bit(m, px, s * kTileRows + r);
+        }
+      }
+    }
     if (!blocked_u) return false;
     // downwards the ray first leaves through the component's own pixels; a later foreground pixel may still
     // belong to the component itself, so a blocked ray proves nothing — fall through to the exact test.

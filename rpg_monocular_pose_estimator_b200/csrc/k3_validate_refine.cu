@@ -16,6 +16,7 @@
 #include "mpe_internal.cuh"
 #include "p3p_device.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace mpe {
 
@@ -427,6 +428,164 @@ __global__ void __launch_bounds__(kK3aThreads) check_kernel(const K3Args a, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3a' — check_wide_kernel: the same computation for SMALL batches (single cameras).  With a thread per subset the
+// kernel's duration is one thread's chain: P3P set-up + four back-substitutions and scorings (61 us for one frame).  Here a
+// CTA serves one frame, warp j evaluates solution j of every subset (lane = subset), so the chain is set-up + ONE solution;
+// warp 0 then picks each subset's best valid solution in solution order (same strict '<' rule), forms its contribution, and
+// one thread adds the contributions in subset order.  Identical arithmetic per value, hence identical results.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWideThreads = 128;     // 4 warps = the 4 P3P solutions
+
+__global__ void __launch_bounds__(kWideThreads) check_wide_kernel(const K3Args a) {
+  extern __shared__ __align__(16) uint8_t k3w_smem[];
+  const int n_obj = a.pp.n_obj;
+  CheckFrame& F = *reinterpret_cast<CheckFrame*>(k3w_smem);
+  double* sq_s = reinterpret_cast<double*>(k3w_smem + sizeof(CheckFrame));          // [4][32] squared error of solution j, subset lane
+  int* valid_s = reinterpret_cast<int*>(sq_s + 4 * 32);                              // [4][32] certainty >= threshold
+  double* contrib = reinterpret_cast<double*>(valid_s + 4 * 32);                     // [32][n_obj*3]
+  int* found_s = reinterpret_cast<int*>(contrib + (size_t)32 * n_obj * 3);           // [32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.x;
+  const double* K = a.cam.K;
+  const double* mk = a.pp.markers;
+  if (a.active && !a.active[f]) return;                       // uniform over the CTA
+
+  if (tid == 0) {
+    int n_det = a.n_det[f], k = a.n_corr[f];
+    if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;
+    if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
+    F.valid = 1; F.k = k;
+    F.N = (k >= 4) ? k * (k - 1) * (k - 2) / 6 : 0;           // pose_estimator.cpp:401
+  }
+  if (tid < MPE_MAX_DET) {
+    const int l = tid;
+    const int n_det = a.n_det[f];
+    if (l < n_det && n_det <= MPE_MAX_DET) {
+      const double* det = a.det + (size_t)f * a.det_stride * 2;
+      double u = det[2 * l], v = det[2 * l + 1];
+      F.det[l][0] = u; F.det[l][1] = v;
+      double x = (u - K[2]) / K[0], y = (v - K[5]) / K[4], z = 1;         // calculateImageVectors :288-301
+      double n = sqrt(x * x + y * y + z * z);
+      F.bearing[l][0] = x / n; F.bearing[l][1] = y / n; F.bearing[l][2] = z / n;
+    }
+    const int k = a.n_corr[f];
+    if (l < k && l < MPE_MAX_LEDS) {
+      F.corr[l][0] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * l];
+      F.corr[l][1] = a.corr[(size_t)f * 2 * MPE_MAX_LEDS + 2 * l + 1];
+    }
+  }
+  __syncthreads();
+
+  const int N = F.N, k = F.k, nu = k - 3;
+  const int n_pass = (N + 31) / 32;
+  double mean[MPE_MAX_LEDS][3];
+  int num_valid = 0;
+  if (tid == 0)
+    for (int j = 0; j < n_obj; ++j) mean[j][0] = mean[j][1] = mean[j][2] = 0;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int i = pass * 32 + lane;                            // subset
+    const int j = warp;                                        // solution
+    P3PSetup S;
+    int rc = -1, c0 = 0, c1 = 0, c2 = 0;
+    double sq = 0;
+    int valid = 0;
+    if (i < N) {
+      unrank_comb3_k3(k, i, c0, c1, c2);
+      const int l0 = F.corr[c0][0] - 1, l1 = F.corr[c1][0] - 1, l2 = F.corr[c2][0] - 1;
+      const int e0 = F.corr[c0][1] - 1, e1 = F.corr[c1][1] - 1, e2 = F.corr[c2][1] - 1;
+      rc = p3p_setup(v_make(F.bearing[e0][0], F.bearing[e0][1], F.bearing[e0][2]),
+                     v_make(F.bearing[e1][0], F.bearing[e1][1], F.bearing[e1][2]),
+                     v_make(F.bearing[e2][0], F.bearing[e2][1], F.bearing[e2][2]),
+                     v_make(mk[3 * l0], mk[3 * l0 + 1], mk[3 * l0 + 2]), v_make(mk[3 * l1], mk[3 * l1 + 1], mk[3 * l1 + 2]),
+                     v_make(mk[3 * l2], mk[3 * l2 + 1], mk[3 * l2 + 2]), S);
+      if (rc == 0) {
+        double H[12];
+        if (p3p_solution(S, j, H) && h_is_finite(H)) {           // :479
+          double Hi[12], KT[12];
+          h_inverse(H, Hi);
+          kt_product(K, Hi, KT);
+          double bu[kMaxUnused], bv[kMaxUnused];
+          double dist[kMaxUnused * kMaxUnused];
+          int m = 0;
+          for (int l = 0; l < k; ++l) {                          // unused rows, in row order (:437-455)
+            if (l == c0 || l == c1 || l == c2) continue;
+            int led = F.corr[l][0] - 1;
+            kt_project(KT, mk[3 * led], mk[3 * led + 1], mk[3 * led + 2], bu[m], bv[m]);
+            ++m;
+          }
+          int ii = 0;
+          for (int l = 0; l < k; ++l) {
+            if (l == c0 || l == c1 || l == c2) continue;
+            int di = F.corr[l][1] - 1;
+            for (int jj = 0; jj < nu; ++jj) {
+              double dx = F.det[di][0] - bu[jj], dy = F.det[di][1] - bv[jj];
+              dist[ii * nu + jj] = sqrt(dx * dx + dy * dy);
+            }
+            ++ii;
+          }
+          double certainty;
+          sq = squared_error_and_certainty(dist, nu, nu, a.pp.back_projection_pixel_tolerance, &certainty);
+          valid = (certainty >= a.pp.certainty_threshold) ? 1 : 0;  // :494
+        }
+      }
+    }
+    sq_s[j * 32 + lane] = sq;
+    valid_s[j * 32 + lane] = valid;
+    __syncthreads();
+    if (warp == 0) {
+      int found = 0;
+      if (i < N && rc == 0) {
+        double min_sq = HUGE_VAL;
+        int best = 0;
+        for (int jj = 0; jj < 4; ++jj) {
+          if (!valid_s[jj * 32 + lane]) continue;
+          found = 1;
+          const double sj = sq_s[jj * 32 + lane];
+          if (sj < min_sq) { min_sq = sj; best = jj; }
+        }
+        if (found) {                                             // :506-518
+          double H[12], Hi[12];
+          p3p_solution(S, best, H);
+          h_inverse(H, Hi);
+          double* out = contrib + (size_t)lane * n_obj * 3;
+          for (int jj = 0; jj < n_obj; ++jj) {
+            double x = mk[3 * jj], y = mk[3 * jj + 1], z = mk[3 * jj + 2];
+            for (int r = 0; r < 3; ++r) {
+              double sacc = Hi[4 * r] * x;
+              sacc += Hi[4 * r + 1] * y;
+              sacc += Hi[4 * r + 2] * z;
+              sacc += Hi[4 * r + 3] * 1.0;
+              out[jj * 3 + r] = sacc;
+            }
+          }
+        }
+      }
+      found_s[lane] = found;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int cnt = min(32, N - pass * 32);
+      for (int jx = 0; jx < cnt; ++jx) {
+        if (!found_s[jx]) continue;
+        ++num_valid;
+        const double* cj = contrib + (size_t)jx * n_obj * 3;
+        for (int jj = 0; jj < n_obj; ++jj)
+          for (int r = 0; r < 3; ++r) mean[jj][r] = mean[jj][r] + cj[jj * 3 + r];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double* so = a.check_sums + (size_t)f * MPE_MAX_LEDS * 3;
+    for (int jj = 0; jj < n_obj; ++jj)
+      for (int r = 0; r < 3; ++r) so[jj * 3 + r] = mean[jj][r];
+    a.check_cnt[2 * f] = num_valid;
+    a.check_cnt[2 * f + 1] = N;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3b — refine_kernel: one THREAD per frame: acceptance test + Kabsch of checkCorrespondences, then the
 // Gauss-Newton of optimisePose, every sum in the reference's loop order.
 // ------------------------------------------------------------------------------------------------
@@ -545,8 +704,272 @@ __global__ void __launch_bounds__(kK3bThreads) refine_kernel(const K3Args a) {
   if (a.updated) a.updated[f] = (ok && ran_gn) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3c — gauss_newton_kernel: PoseEstimator::optimisePose (pose_estimator.cpp:733-792) with a GROUP of G lanes per frame.
+// The thread-per-frame version above is a ~100 us serial chain per frame (5 iterations x [5 Jacobians with 10 divisions each,
+// a pivoted 6x6 LDL^T with 56 divisions, an exponential map]) and keeps fewer than two warps per SM busy at 8192 frames.
+// Here, per iteration:
+//   1. lane j computes project2d, the residual and the two Jacobian rows of correspondence j       (:759-772, :932-960)
+//   2. lane e owns entry e of (A, b) — 21 unique entries of the symmetric A, 6 of b — and sums the contributions of the
+//      correspondences IN CORRESPONDENCE ORDER, i.e. exactly the reference's  A += J^T J,  b += J^T e  (:774-775)
+//   3. the pivoted LDL^T (:778) runs with the Schur updates of one elimination step spread over the lanes; row/column
+//      exchanges are a permutation held in a register, so no data moves.  Every entry sees the same operations in the same
+//      order as oracle ldlt_solve6 / the serial ldlt_solve6 above, hence identical bits and identical iteration counts
+//   4. exponential map and pose update (:781): the 9 + 9 entries of R and V over the lanes
+// and at the end the covariance A^-1 (:790) by the same Gauss-Jordan as inverse6 with one tableau column per lane.
+// G = 8 (four frames per warp) for large batches, G = 32 when few frames are in flight (single-camera latency).
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 64;
+constexpr int kGnCooperativeMaxFrames = 1024;
+
+struct GnScratch {
+  double J[MPE_MAX_LEDS][14];   // per correspondence: J0[6], J1[6], e0, e1
+  double A0[36];                // normal matrix of the current iteration (kept: the covariance is its inverse)
+  double Aw[36];                // working copy, factorised in place
+  double b[6], dT[6];
+  double T[12];                 // pose, top three rows, row-major
+  double rv[18];                // R[9], V[9] of the exponential map
+  double tab[72];               // 6 x 12 Gauss-Jordan tableau
+  int used[MPE_MAX_LEDS];
+};
+
+__device__ __forceinline__ int nib(uint32_t pk, int i) { return (int)((pk >> (4 * i)) & 15u); }
+__device__ __forceinline__ uint32_t nib_swap(uint32_t pk, int i, int j) {
+  const uint32_t a = (pk >> (4 * i)) & 15u, b = (pk >> (4 * j)) & 15u;
+  pk &= ~((15u << (4 * i)) | (15u << (4 * j)));
+  return pk | (b << (4 * i)) | (a << (4 * j));
+}
+
+template <int G>
+__global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a, int gate_on_ok) {
+  constexpr int kGroups = kGnThreads / G;
+  __shared__ GnScratch scratch[kGroups];
+  const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+  const int f = blockIdx.x * kGroups + gid;
+  if (f >= a.n_frames) return;                                   // uniform per group from here on
+  if (a.active && !a.active[f]) return;
+  if (gate_on_ok && !a.ok[f]) return;                            // checkCorrespondences failed: no optimisePose
+  GnScratch& S = scratch[gid];
+  const double* K = a.cam.K;
+  const double* mk = a.pp.markers;
+  const int n_det = a.n_det[f];
+  int k = a.n_corr[f];
+  if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;
+  if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
+  const double* det = a.det + (size_t)f * a.det_stride * 2;
+  const uint32_t* corr = a.corr + (size_t)f * 2 * MPE_MAX_LEDS;
+  const double fx = K[0], fy = K[4];
+
+  for (int e = gl; e < 12; e += G) S.T[e] = a.pose_io[(size_t)f * 16 + e];
+  for (int e = gl; e < 36; e += G) S.A0[e] = 0;
+  __syncwarp(gmask);
+
+  int iters = 0;
+  for (int it = 0; it < 500; ++it) {                               // max_itr :738
+    double T[12], KT[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = S.T[e];
+    kt_product(K, T, KT);                                          // project2d :251-268 (same KT for every point)
+    // ---- 1. one correspondence per lane
+    for (int j = gl; j < k; j += G) {
+      const uint32_t led1 = corr[2 * j], det1 = corr[2 * j + 1];
+      S.used[j] = (det1 != 0);                                     // :761
+      if (det1 == 0) continue;
+      const int led = (int)led1 - 1, di = (int)det1 - 1;
+      const double ox = mk[3 * led], oy = mk[3 * led + 1], oz = mk[3 * led + 2];
+      double pu, pv;
+      kt_project(KT, ox, oy, oz, pu, pv);
+      const double e0 = det[2 * di] - pu, e1 = det[2 * di + 1] - pv;   // :769
+      // computeJacobian :932-960
+      const double x = T[0] * ox + T[1] * oy + T[2] * oz + T[3] * 1.0;
+      const double y = T[4] * ox + T[5] * oy + T[6] * oz + T[7] * 1.0;
+      const double z = T[8] * ox + T[9] * oy + T[10] * oz + T[11] * 1.0;
+      const double z_2 = z * z;
+      double* Jj = S.J[j];
+      Jj[0] = 1 / z * fx; Jj[1] = 0; Jj[2] = -x / z_2 * fx; Jj[3] = -x * y / z_2 * fx; Jj[4] = (1 + (x * x / z_2)) * fx; Jj[5] = -y / z * fx;
+      Jj[6] = 0; Jj[7] = 1 / z * fy; Jj[8] = -y / z_2 * fy; Jj[9] = -(1 + y * y / z_2) * fy; Jj[10] = x * y / z_2 * fy; Jj[11] = x / z * fy;
+      Jj[12] = e0; Jj[13] = e1;
+    }
+    __syncwarp(gmask);
+    // ---- 2. one entry of (A, b) per lane, contributions added in correspondence order
+    for (int e = gl; e < 27; e += G) {
+      double acc = 0;
+      if (e < 21) {
+        int r = 0, c = e;                                          // e -> (r, c), c <= r, rows of the lower triangle one after another
+        while (c > r) { c -= r + 1; ++r; }
+        for (int j = 0; j < k; ++j) {
+          if (!S.used[j]) continue;
+          const double* Jj = S.J[j];
+          acc += Jj[r] * Jj[c] + Jj[6 + r] * Jj[6 + c];
+        }
+        S.A0[r * 6 + c] = acc; S.A0[c * 6 + r] = acc;              // J0[r]*J0[c] == J0[c]*J0[r]: the reference's two entries are equal
+        S.Aw[r * 6 + c] = acc; S.Aw[c * 6 + r] = acc;
+      } else {
+        const int r = e - 21;
+        for (int j = 0; j < k; ++j) {
+          if (!S.used[j]) continue;
+          const double* Jj = S.J[j];
+          acc += Jj[r] * Jj[12] + Jj[6 + r] * Jj[13];
+        }
+        S.b[r] = acc;
+      }
+    }
+    __syncwarp(gmask);
+    // ---- 3. dT = A.ldlt().solve(b)  (:778), arithmetic of ldlt_solve6
+    uint32_t pk = 0x543210u;                                       // perm[i] = nibble i
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk) {
+      int p = kk;
+      double best = fabs(S.Aw[nib(pk, kk) * 7]);
+#pragma unroll
+      for (int i = kk + 1; i < 6; ++i) {
+        const double v = fabs(S.Aw[nib(pk, i) * 7]);
+        if (v > best) { best = v; p = i; }
+      }
+      pk = nib_swap(pk, kk, p);
+      const int pkk = nib(pk, kk);
+      const double d = S.Aw[pkk * 7];
+      const int n_tr = 5 - kk, n_pairs = n_tr * (n_tr + 1) / 2;
+      for (int e = gl; e < n_pairs; e += G) {                       // Schur update of the trailing lower triangle (column kk still unscaled)
+        int io = 0, jo = e;
+        while (jo > io) { jo -= io + 1; ++io; }
+        const int pi = nib(pk, kk + 1 + io), pj = nib(pk, kk + 1 + jo);
+        const double v = S.Aw[pi * 6 + pj] - S.Aw[pi * 6 + pkk] * S.Aw[pj * 6 + pkk] / d;
+        S.Aw[pi * 6 + pj] = v; S.Aw[pj * 6 + pi] = v;
+      }
+      __syncwarp(gmask);
+      for (int i = kk + 1 + gl; i < 6; i += G) { const int pi = nib(pk, i); S.Aw[pi * 6 + pkk] = S.Aw[pi * 6 + pkk] / d; }   // L(i,kk)
+      __syncwarp(gmask);
+    }
+    double dT[6];
+    {
+      double y[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) y[i] = S.b[nib(pk, i)];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) y[i] -= S.Aw[nib(pk, i) * 6 + nib(pk, j)] * y[j];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) y[i] /= S.Aw[nib(pk, i) * 7];
+#pragma unroll
+      for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) y[i] -= S.Aw[nib(pk, j) * 6 + nib(pk, i)] * y[j];
+      if (gl == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) S.dT[nib(pk, i)] = y[i];
+      }
+      __syncwarp(gmask);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dT[i] = S.dT[i];
+    }
+    // ---- 4. T <- exp(dT) * T  (:781, :962-994), arithmetic of exp_map_left_multiply
+    {
+      const double ux = dT[0], uy = dT[1], uz = dT[2], wx = dT[3], wy = dT[4], wz = dT[5];
+      const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+      const double theta_squared = theta * theta;
+      double sn = 0, cs = 0, kv1 = 0, kv2 = 0;
+      if (theta != 0) {
+        sn = sin(theta); cs = cos(theta);
+        kv1 = (1 - cs) / (theta_squared); kv2 = (theta - sn) / (theta_squared * theta);
+      }
+      for (int e = gl; e < 9; e += G) {
+        const int i = e / 3, j = e - 3 * i;
+        // row i and column j of O = [w]x (selects, no run-time indexed local arrays)
+        const double Oi0 = i == 0 ? 0.0 : (i == 1 ? wz : -wy), Oi1 = i == 0 ? -wz : (i == 1 ? 0.0 : wx), Oi2 = i == 0 ? wy : (i == 1 ? -wx : 0.0);
+        const double Oj0 = j == 0 ? 0.0 : (j == 1 ? -wz : wy), Oj1 = j == 0 ? wz : (j == 1 ? 0.0 : -wx), Oj2 = j == 0 ? -wy : (j == 1 ? wx : 0.0);
+        const double Oij = j == 0 ? Oi0 : (j == 1 ? Oi1 : Oi2);
+        const double O2ij = Oi0 * Oj0 + Oi1 * Oj1 + Oi2 * Oj2;
+        const double I = (i == j) ? 1.0 : 0.0;
+        double r_ij = I, v_ij = I;
+        if (theta != 0) {
+          r_ij = I + Oij / theta * sn + O2ij / theta_squared * (1 - cs);
+          v_ij = I + kv1 * Oij + kv2 * O2ij;
+        }
+        S.rv[e] = r_ij; S.rv[9 + e] = v_ij;
+      }
+      __syncwarp(gmask);
+      for (int e = gl; e < 12; e += G) {
+        const int i = e >> 2, j = e & 3;
+        const double ti = S.rv[9 + 3 * i] * ux + S.rv[9 + 3 * i + 1] * uy + S.rv[9 + 3 * i + 2] * uz;
+        const double bottom = (j == 3) ? 1.0 : 0.0;
+        const double T0j = j == 0 ? T[0] : (j == 1 ? T[1] : (j == 2 ? T[2] : T[3]));
+        const double T1j = j == 0 ? T[4] : (j == 1 ? T[5] : (j == 2 ? T[6] : T[7]));
+        const double T2j = j == 0 ? T[8] : (j == 1 ? T[9] : (j == 2 ? T[10] : T[11]));
+        double sacc = S.rv[3 * i] * T0j;
+        sacc += S.rv[3 * i + 1] * T1j;
+        sacc += S.rv[3 * i + 2] * T2j;
+        sacc += ti * bottom;
+        S.T[e] = sacc;
+      }
+      __syncwarp(gmask);
+    }
+    ++iters;
+    double mx = -1;                                                 // norm_max :1073-1085
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { const double av = fabs(dT[q]); if (av > mx) mx = av; }
+    if (mx <= 1e-13) break;                                         // :786
+  }
+
+  // ---- covariance = A^-1 of the last iteration (:790), arithmetic of inverse6; the row exchanges are a permutation
+  for (int e = gl; e < 72; e += G) { const int i = e / 12, j = e - 12 * i; S.tab[e] = (j < 6) ? S.A0[i * 6 + j] : ((j - 6 == i) ? 1.0 : 0.0); }
+  __syncwarp(gmask);
+  uint32_t rp = 0x543210u;
+#pragma unroll
+  for (int kk = 0; kk < 6; ++kk) {
+    int p = kk;
+    double best = fabs(S.tab[nib(rp, kk) * 12 + kk]);
+#pragma unroll
+    for (int i = kk + 1; i < 6; ++i) {
+      const double v = fabs(S.tab[nib(rp, i) * 12 + kk]);
+      if (v > best) { best = v; p = i; }
+    }
+    rp = nib_swap(rp, kk, p);
+    const int rk = nib(rp, kk);
+    const double pv = S.tab[rk * 12 + kk];
+    __syncwarp(gmask);                                              // everybody has read the pivot before the row is scaled
+    for (int j = gl; j < 12; j += G) S.tab[rk * 12 + j] = S.tab[rk * 12 + j] / pv;
+    __syncwarp(gmask);
+    double fct[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) fct[i] = S.tab[nib(rp, i) * 12 + kk];
+    __syncwarp(gmask);                                              // factors read before column kk is overwritten
+    for (int e = gl; e < 72; e += G) {
+      const int i = e / 12, j = e - 12 * i;
+      if (i == kk) continue;
+      const double fi = (i == 0) ? fct[0] : (i == 1) ? fct[1] : (i == 2) ? fct[2] : (i == 3) ? fct[3] : (i == 4) ? fct[4] : fct[5];
+      if (fi != 0) { const int ri = nib(rp, i); S.tab[ri * 12 + j] = S.tab[ri * 12 + j] - fi * S.tab[rk * 12 + j]; }
+    }
+    __syncwarp(gmask);
+  }
+  if (a.cov)
+    for (int e = gl; e < 36; e += G) { const int i = e / 6, j = e - 6 * i; a.cov[(size_t)f * 36 + e] = S.tab[nib(rp, i) * 12 + 6 + j]; }
+  double* po = a.pose_io + (size_t)f * 16;
+  for (int e = gl; e < 12; e += G) po[e] = S.T[e];
+  if (gl == 0) {
+    po[12] = 0; po[13] = 0; po[14] = 0; po[15] = 1;
+    if (a.ok) a.ok[f] = 1;
+    if (a.iters) a.iters[f] = iters;
+    if (a.updated) a.updated[f] = 1;
+  }
+}
+
+static bool wide_ok() {      // MPE_K3_WIDE=0 keeps the thread-per-subset check kernel for every batch size
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MPE_K3_WIDE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
-  if (a.mode == 0 || a.mode == 1) {
+  if ((a.mode == 0 || a.mode == 1) && a.n_frames <= kGnCooperativeMaxFrames && wide_ok()) {
+    const int n_obj = a.pp.n_obj;
+    size_t smem = sizeof(CheckFrame) + 4 * 32 * (sizeof(double) + sizeof(int)) + (size_t)32 * n_obj * 3 * sizeof(double) + 32 * sizeof(int);
+    check_wide_kernel<<<a.n_frames, kWideThreads, smem, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else if (a.mode == 0 || a.mode == 1) {
     const int n_obj = a.pp.n_obj;
     int Nmax = (n_obj >= 4) ? n_obj * (n_obj - 1) * (n_obj - 2) / 6 : 1;
     int G = (Nmax <= kK3aThreads) ? kK3aThreads / Nmax : 1;
@@ -563,7 +986,30 @@ cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(a);
+  // Gauss-Newton layout.  Measured on B200: one frame takes 105 us with a thread per frame and 36.5 us with 32 lanes per frame,
+  // but at 8192 frames the thread-per-frame kernel (every lane busy, 0.25 ms) beats 8 or 32 lanes per frame (0.22 / 0.27 ms plus
+  // the separate Kabsch launch) — so the lane-cooperative kernel serves small batches (single cameras), the serial one large ones.
+  // MPE_K3_GN overrides: 0 = always thread per frame, 8 / 32 = always that many lanes per frame.
+  static int gn_mode = -1;
+  if (gn_mode < 0) { const char* e = getenv("MPE_K3_GN"); gn_mode = e ? atoi(e) : -2; }
+  const bool cooperative = (gn_mode == 8 || gn_mode == 32) || (gn_mode != 0 && a.n_frames <= kGnCooperativeMaxFrames);
+  if (!cooperative || a.mode == 1) {
+    refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  // mode 0: acceptance test + Kabsch with a thread per frame (refine_kernel in check-only mode), then the lane-cooperative
+  // Gauss-Newton for the frames it accepted; mode 2: Gauss-Newton only
+  if (a.mode == 0) {
+    K3Args chk = a;
+    chk.mode = 1;
+    refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(chk);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  const int gate = (a.mode == 0) ? 1 : 0;
+  const int lanes = (gn_mode == 8) ? 8 : 32;
+  if (lanes == 32) gauss_newton_kernel<32><<<(a.n_frames + 1) / 2, kGnThreads, 0, st>>>(a, gate);
+  else gauss_newton_kernel<8><<<(a.n_frames + 7) / 8, kGnThreads, 0, st>>>(a, gate);
   return cudaGetLastError();
 }
 

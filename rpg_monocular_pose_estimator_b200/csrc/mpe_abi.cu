@@ -357,7 +357,7 @@ int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const ui
   time_begin(c, 3, st);
   CUDA_TRY(c, launch_validate_refine(k, st));
   time_end(c, 3, st);
-  c->launches += (mode == 2) ? 1 : 2;
+  c->launches += (mode == 2) ? 1 : ((mode == 1 || n > 1024) ? 2 : 3);   // check + Kabsch/GN in one kernel, or check + Kabsch + cooperative GN for small batches
   return MPE_OK;
 }
 
