@@ -152,7 +152,7 @@ def usable_cores():
     return n
 
 
-def cpu_single_thread(scene, max_seconds=15.0, max_frames=4000):
+def cpu_single_thread(scene, max_seconds=12.0, max_frames=20000):
     import cv2
     cv2.setNumThreads(1)
     from oracle import pose_oracle
@@ -294,18 +294,19 @@ def run_tracking(args):
         import cv2
         cv2.setNumThreads(1)
         from oracle import pose_oracle
-        n_cpu = 1500
+        n_cpu = 1200
         sc = synth.make_stream_scene(n_cpu, n_leds=args.leds, width=W, height=H, seed=args.seed + 5)     # one long continuous trajectory
         est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
-        for tt_ in range(8):
-            est.estimate_body_pose(sc.frames[tt_], sc.times[tt_])
+        # the trajectory is played forwards and backwards (continuous motion, monotonic time stamps) until ~10 s have passed
+        order = list(range(n_cpu)) + list(range(n_cpu - 2, 0, -1))
+        tcur = 0.0
+        for i in range(8):
+            est.estimate_body_pose(sc.frames[order[i]], tcur); tcur += 1 / 60.0
         t0c = time.perf_counter()
-        n = 0
-        for tt_ in range(8, n_cpu):
-            est.estimate_body_pose(sc.frames[tt_], sc.times[tt_])
-            n += 1
-            if time.perf_counter() - t0c > 12:
-                break
+        n, i = 0, 8
+        while time.perf_counter() - t0c < 10.0:
+            est.estimate_body_pose(sc.frames[order[i % len(order)]], tcur); tcur += 1 / 60.0
+            i += 1; n += 1
         dtc = time.perf_counter() - t0c
         line["cpu_baseline"] = {"value": n / dtc, "unit": "frames/s", "cores": 1, "kind": "port",
                                 "sample": f"{n} tracking-mode frames in {dtc:.1f} s, one thread (cv2 4.13 findLeds on the ROI + C++ oracle)"}

@@ -702,6 +702,10 @@ __global__ void __launch_bounds__(kK3bThreads) refine_kernel(const K3Args a) {
   if (a.ok) a.ok[f] = ok;
   if (a.iters) a.iters[f] = iters;
   if (a.updated) a.updated[f] = (ok && ran_gn) ? 1 : 0;
+  if (a.mode == 1) {                       // tracking loop: route the stream to optimisePose or to initialise()
+    if (ok) { if (a.set_gn_if_ok) a.set_gn_if_ok[f] = 1; }
+    else if (a.set_init_if_fail) a.set_init_if_fail[f] = 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

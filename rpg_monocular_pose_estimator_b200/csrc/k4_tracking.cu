@@ -214,9 +214,7 @@ __global__ void track_begin_kernel(const TrackArgs a) {
 }
 
 // ---- step 2 (pass 0) / 2' (pass 1): what to do with the detections -----------------------------------------------
-__global__ void track_after_detect_kernel(const TrackArgs a, int pass) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.n) return;
+__device__ __forceinline__ void track_after_detect_body(const TrackArgs& a, int pass, int s) {
   if (a.done[s]) return;
   if (pass == 1 && !a.a_retry[s]) return;
   const int n = a.n_det[s];
@@ -259,30 +257,23 @@ __global__ void track_after_detect_kernel(const TrackArgs a, int pass) {
   }
 }
 
-// pass 0 leaves ROIs for everybody; before the retry detection the ROI of streams that do not retry must be empty
-__global__ void track_prepare_retry_kernel(const TrackArgs a) {
+__global__ void track_after_detect_kernel(const TrackArgs a, int pass) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n) return;
+  track_after_detect_body(a, pass, s);
+}
+
+// pass 0 wrapper: afterwards the ROI of every stream that does not retry is emptied, so that the retry launches of K1 find no
+// tile to work on for it
+__global__ void track_after_detect0_kernel(const TrackArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n) return;
+  track_after_detect_body(a, 0, s);
   if (!a.a_retry[s]) { Roi none; none.x = 0; none.y = 0; none.w = 0; none.h = 0; a.rois[s] = none; }
 }
 
-// ---- step 3: after checkCorrespondences on the NN correspondences (:835-846) -------------------------------------
-__global__ void track_after_check_kernel(const TrackArgs a) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.n) return;
-  if (!a.a_check[s]) return;
-  if (a.ok[s]) a.a_gn[s] = 1;
-  else a.a_init[s] = 1;                                              // re-initialise with the brute-force search
-}
-
-// ---- step 4: after initialise() -----------------------------------------------------------------------------------
-__global__ void track_after_init_kernel(const TrackArgs a) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.n) return;
-  if (!a.a_init[s]) return;
-  a.track_flags[s] |= MPE_F_INITIALISED;
-  if (a.ok[s]) a.a_gn[s] = 1;
-}
+// (steps 3 and 4 — "checkCorrespondences succeeded -> optimisePose, else initialise()" (:835-846) and "initialise() succeeded ->
+//  optimisePose" — are written by the check kernel's epilogue: K3Args::set_gn_if_ok / set_init_if_fail.)
 
 // ---- step 5: optimiseAndUpdatePose bookkeeping (:802-812, :794-800) + result records ------------------------------
 __global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
@@ -304,7 +295,7 @@ __global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
   r.n_det = a.n_det[s];
   r.n_corr = a.n_corr[s];
   r.gn_iters = a.iters[s];
-  r.flags = a.flags[s] | a.track_flags[s];
+  r.flags = a.flags[s] | a.track_flags[s] | (a.a_init[s] ? MPE_F_INITIALISED : 0);
   r.init_ok = a.ok[s];
   const Roi roi = a.result_rois[s];
   r.roi.x = roi.x; r.roi.y = roi.y; r.roi.width = roi.w; r.roi.height = roi.h;
@@ -332,10 +323,11 @@ __global__ void track_reset_kernel(StreamState* st, int n) {
 static inline int grid_for(int n) { return (n + 127) / 128; }
 
 cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st) { track_begin_kernel<<<grid_for(a.n), 128, 0, st>>>(a); return cudaGetLastError(); }
-cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st) { track_after_detect_kernel<<<grid_for(a.n), 128, 0, st>>>(a, pass); return cudaGetLastError(); }
-cudaError_t launch_track_prepare_retry(const TrackArgs& a, cudaStream_t st) { track_prepare_retry_kernel<<<grid_for(a.n), 128, 0, st>>>(a); return cudaGetLastError(); }
-cudaError_t launch_track_after_check(const TrackArgs& a, cudaStream_t st) { track_after_check_kernel<<<grid_for(a.n), 128, 0, st>>>(a); return cudaGetLastError(); }
-cudaError_t launch_track_after_init(const TrackArgs& a, cudaStream_t st) { track_after_init_kernel<<<grid_for(a.n), 128, 0, st>>>(a); return cudaGetLastError(); }
+cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st) {
+  if (pass == 0) track_after_detect0_kernel<<<grid_for(a.n), 128, 0, st>>>(a);
+  else track_after_detect_kernel<<<grid_for(a.n), 128, 0, st>>>(a, pass);
+  return cudaGetLastError();
+}
 cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st) { track_finish_kernel<<<grid_for(a.n), 128, 0, st>>>(a, out); return cudaGetLastError(); }
 cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st) { track_reset_kernel<<<grid_for(n), 128, 0, st>>>(s, n); return cudaGetLastError(); }
 

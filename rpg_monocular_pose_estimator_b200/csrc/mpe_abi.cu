@@ -335,7 +335,8 @@ int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* acti
   return MPE_OK;
 }
 
-int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const uint8_t* active) {
+int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const uint8_t* active, uint8_t* set_gn_if_ok = nullptr,
+               uint8_t* set_init_if_fail = nullptr) {
   K3Args k{};
   k.n_frames = n;
   k.n_det = c->d.n_det + slot0;
@@ -354,6 +355,8 @@ int run_refine(mpe_ctx* c, int slot0, int n, int mode, cudaStream_t st, const ui
   k.active = active;
   k.check_sums = c->d.check_sums + (size_t)slot0 * MPE_MAX_LEDS * 3;
   k.check_cnt = c->d.check_cnt + (size_t)slot0 * 2;
+  k.set_gn_if_ok = set_gn_if_ok;
+  k.set_init_if_fail = set_init_if_fail;
   time_begin(c, 3, st);
   CUDA_TRY(c, launch_validate_refine(k, st));
   time_end(c, 3, st);
@@ -873,23 +876,20 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   CUDA_TRY(c, launch_track_begin(t, st));                                                        // predictWithROI
   rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, nullptr);   // findLeds(ROI)
   if (rc != MPE_OK) return rc;
-  CUDA_TRY(c, launch_track_after_detect(t, 0, st));
-  CUDA_TRY(c, launch_track_prepare_retry(t, st));
+  CUDA_TRY(c, launch_track_after_detect(t, 0, st));                                              // + empties the ROI of streams that do not retry
   rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, t.a_retry);  // whole-image retry (only where needed)
   if (rc != MPE_OK) return rc;
   CUDA_TRY(c, launch_track_after_detect(t, 1, st));
-  rc = run_refine(c, 0, n, 1, st, t.a_check);                                                    // checkCorrespondences on the NN matches
+  rc = run_refine(c, 0, n, 1, st, t.a_check, t.a_gn, t.a_init);                                  // checkCorrespondences on the NN matches; ok -> GN, else -> initialise()
   if (rc != MPE_OK) return rc;
-  CUDA_TRY(c, launch_track_after_check(t, st));
   rc = run_sweep(c, 0, n, st, t.a_init);                                                         // initialise(): cold streams + failed checks
   if (rc != MPE_OK) return rc;
-  rc = run_refine(c, 0, n, 1, st, t.a_init);
+  rc = run_refine(c, 0, n, 1, st, t.a_init, t.a_gn, nullptr);                                    // its check; ok -> GN
   if (rc != MPE_OK) return rc;
-  CUDA_TRY(c, launch_track_after_init(t, st));
   rc = run_refine(c, 0, n, 2, st, t.a_gn);                                                       // optimisePose
   if (rc != MPE_OK) return rc;
   CUDA_TRY(c, launch_track_finish(t, c->d.results, st));
-  c->launches += 7;
+  c->launches += 4;
   return MPE_OK;
 }
 

@@ -129,6 +129,9 @@ struct K3Args {
   const uint8_t* active;     // optional
   double* check_sums;        // [n_frames][MPE_MAX_LEDS*3]  sum of H^-1 X_j over the valid subsets (K3a -> K3b)
   int* check_cnt;            // [n_frames][2]  number of valid subsets, number of subsets
+  // tracking loop (mode 1 only): what follows from the outcome of checkCorrespondences, written per frame by refine_kernel
+  uint8_t* set_gn_if_ok;     // optional [n_frames]: set to 1 when the check succeeded (-> optimisePose)
+  uint8_t* set_init_if_fail; // optional [n_frames]: set to 1 when it failed (-> brute-force initialise(), pose_estimator.cpp:842)
 };
 
 // Per-stream state of the tracking loop = the PoseEstimator members that survive a frame (pose_estimator.h:56-79)
@@ -159,9 +162,6 @@ struct TrackArgs {
 // ---- launchers (defined next to the kernels) ----
 cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st);
 cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st);
-cudaError_t launch_track_prepare_retry(const TrackArgs& a, cudaStream_t st);
-cudaError_t launch_track_after_check(const TrackArgs& a, cudaStream_t st);
-cudaError_t launch_track_after_init(const TrackArgs& a, cudaStream_t st);
 cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st);
 cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st);
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
