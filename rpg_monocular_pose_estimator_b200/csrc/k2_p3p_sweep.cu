@@ -358,8 +358,11 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
 #pragma unroll
               for (int e = 0; e < 12; ++e) q_h[e][slot] = H[e];
               q_ids[slot] = ids;
-            } else {
-              score_and_vote(H, ids, n_det, n_obj, det, mk, Ks, tol_sq_max, ghist);   // queue full: score in place
+            } else {                                             // queue full: score in place (rare; the copy keeps H itself in registers)
+              double Hc[12];
+#pragma unroll
+              for (int e = 0; e < 12; ++e) Hc[e] = H[e];
+              score_and_vote(Hc, ids, n_det, n_obj, det, mk, Ks, tol_sq_max, ghist);
             }
           }
         }
