@@ -331,14 +331,17 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
           if (ccode & 1) { const int r6 = pj % 6; tj = pj - r6 + ((0x134052 >> (4 * r6)) & 7); }
           const bool filt = a.use_filter && (ccode & 2) && tt[(size_t)15 * n_perm + tj] == 2.0;
           P3PSetup S;
-          S.e1 = v_make(cb[0], cb[1], cb[2]); S.e2 = v_make(cb[3], cb[4], cb[5]); S.e3 = v_make(cb[6], cb[7], cb[8]);
+          // the six scalars the quartic needs first; the 21 frame entries only after it (they would just be spilled across the
+          // ~1000 instructions of the quartic at 80 registers per thread — the barrier keeps the compiler from hoisting the loads)
           S.f_1 = cb[9]; S.f_2 = cb[10]; S.b = cb[11];
+          S.p_1 = tt[(size_t)12 * n_perm + tj]; S.p_2 = tt[(size_t)13 * n_perm + tj]; S.d_12 = tt[(size_t)14 * n_perm + tj];
+          p3p_quartic(S.f_1, S.f_2, S.p_1, S.p_2, S.d_12, S.b, S.roots);
+          asm volatile("" ::: "memory");
+          S.e1 = v_make(cb[0], cb[1], cb[2]); S.e2 = v_make(cb[3], cb[4], cb[5]); S.e3 = v_make(cb[6], cb[7], cb[8]);
           S.n1 = v_make(tt[tj], tt[(size_t)n_perm + tj], tt[(size_t)2 * n_perm + tj]);
           S.n2 = v_make(tt[(size_t)3 * n_perm + tj], tt[(size_t)4 * n_perm + tj], tt[(size_t)5 * n_perm + tj]);
           S.n3 = v_make(tt[(size_t)6 * n_perm + tj], tt[(size_t)7 * n_perm + tj], tt[(size_t)8 * n_perm + tj]);
           S.P1 = v_make(tt[(size_t)9 * n_perm + tj], tt[(size_t)10 * n_perm + tj], tt[(size_t)11 * n_perm + tj]);
-          S.p_1 = tt[(size_t)12 * n_perm + tj]; S.p_2 = tt[(size_t)13 * n_perm + tj]; S.d_12 = tt[(size_t)14 * n_perm + tj];
-          p3p_quartic(S.f_1, S.f_2, S.p_1, S.p_2, S.d_12, S.b, S.roots);
 
           int d0, d1, d2, o0, o1, o2, oa, ob, oc;
           unrank_comb3(n_det, ci, d0, d1, d2);
