@@ -126,6 +126,33 @@ __device__ __forceinline__ TileCoord decode_tile(const K1Geom& g, const TileCurs
   return c;
 }
 
+// listed tile (K1Geom::tile_list): every listed tile is valid
+__device__ __forceinline__ TileCoord decode_listed(const K1Geom& g, uint32_t e, bool want_roi) {
+  TileCoord c;
+  c.f = (int)(e >> 12); c.s = (int)((e >> 5) & 127u); c.ct = (int)(e & 31u);
+  if (want_roi) c.roi = g.rois[c.f];
+  c.valid = true;
+  return c;
+}
+
+// One thread per frame appends the tiles its ROI touches to the work list (order irrelevant: every tile is independent).
+__global__ void build_tile_list_kernel(const K1Geom g, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.n_frames) return;
+  const Roi r = g.rois[f];
+  if (r.w <= 0 || r.h <= 0) return;
+  const int ns = min((r.h + kTileRows - 1) / kTileRows, g.n_strips);
+  const int nc = min((r.w + g.tw_px - 1) / g.tw_px, g.n_ct);
+  uint32_t o = atomicAdd(count, (uint32_t)(ns * nc));
+  for (int s = 0; s < ns; ++s)
+    for (int ct = 0; ct < nc; ++ct) list[o++] = ((uint32_t)f << 12) | ((uint32_t)s << 5) | (uint32_t)ct;
+}
+
+cudaError_t launch_build_tile_list(const K1Geom& g, uint32_t* list, uint32_t* count, cudaStream_t st) {
+  build_tile_list_kernel<<<(g.n_frames + 127) / 128, 128, 0, st>>>(g, list, count);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1a — scan_kernel: the streaming pass.  Persistent CTAs pull (frame, strip, column-tile) boxes through a TMA ring and
 // only answer "which 32-bit words hold a byte above the threshold".  Tiles without such a word (the vast majority of an
@@ -160,7 +187,10 @@ __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_consta
   uint8_t* ring = smem_raw + k1_ring_offset();
 
   const int tid = threadIdx.x;
-  const int n_tiles = g.n_frames * g.n_strips * g.n_ct;
+  const bool listed = g.tile_list != nullptr;
+  const int per_frame = g.n_strips * g.n_ct;
+  const int n_tiles = listed ? (int)*g.tile_count : g.n_frames * per_frame;
+  if (n_tiles == 0) return;                        // e.g. the whole-image retry pass of a tracking step that no stream needs
   if (tid == 0) {
     misc[0] = 0u; misc[1] = 0u;
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -174,7 +204,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_consta
   pcur.init(g, blockIdx.x, gridDim.x);
   auto produce_one = [&]() {
     while (ptile < n_tiles) {
-      TileCoord c = decode_tile(g, pcur);
+      TileCoord c = listed ? decode_listed(g, g.tile_list[ptile], true) : decode_tile(g, pcur);
       ptile += gridDim.x;
       pcur.advance();
       if (!c.valid) continue;
@@ -207,9 +237,15 @@ __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_consta
   uint32_t cparity = 0;
   TileCursor ccur;
   ccur.init(g, blockIdx.x, gridDim.x);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ccur.advance()) {
-    TileCoord c = decode_tile(g, ccur);
-    if (!c.valid) continue;
+  for (int idx = blockIdx.x; idx < n_tiles; idx += gridDim.x, ccur.advance()) {
+    int tile = idx;                                  // id filed with a hot tile: f * per_frame + strip * n_ct + column tile
+    if (listed) {
+      const TileCoord c = decode_listed(g, g.tile_list[idx], false);
+      tile = c.f * per_frame + c.s * g.n_ct + c.ct;
+    } else {
+      const TileCoord c = decode_tile(g, ccur);
+      if (!c.valid) continue;
+    }
     const int stage = cstage;
     const uint32_t parity = cparity;
     if (++cstage == kStages) { cstage = 0; cparity ^= 1u; }

@@ -749,105 +749,124 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
   constexpr int kGroups = kGnThreads / G;
   __shared__ GnScratch scratch[kGroups];
   const int gid = threadIdx.x / G, gl = threadIdx.x % G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
   const int f = blockIdx.x * kGroups + gid;
-  if (f >= a.n_frames) return;                                   // uniform per group from here on
-  if (a.active && !a.active[f]) return;
-  if (gate_on_ok && !a.ok[f]) return;                            // checkCorrespondences failed: no optimisePose
+  // Control flow is WARP-uniform: the groups of a warp run the stages in lock-step and meet at full-mask __syncwarp()s (a
+  // group that only synchronised with its own lanes would never reconverge with its neighbours after the first data-dependent
+  // branch, and the warp would execute its groups one after the other — measured: 4x slower with G = 8).  A group without
+  // work (no frame, inactive, check failed) or one that has converged keeps walking through the stages with `run` false.
+  bool alive = f < a.n_frames;
+  if (alive && a.active && !a.active[f]) alive = false;
+  if (alive && gate_on_ok && !a.ok[f]) alive = false;              // checkCorrespondences failed: no optimisePose
   GnScratch& S = scratch[gid];
   const double* K = a.cam.K;
   const double* mk = a.pp.markers;
-  const int n_det = a.n_det[f];
-  int k = a.n_corr[f];
-  if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;
-  if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
-  const double* det = a.det + (size_t)f * a.det_stride * 2;
-  const uint32_t* corr = a.corr + (size_t)f * 2 * MPE_MAX_LEDS;
+  int k = 0;
+  const double* det = a.det;
+  const uint32_t* corr = a.corr;
+  if (alive) {
+    const int n_det = a.n_det[f];
+    k = a.n_corr[f];
+    if (n_det < 0 || n_det > MPE_MAX_DET) k = 0;
+    if (k > MPE_MAX_LEDS) k = MPE_MAX_LEDS;
+    det = a.det + (size_t)f * a.det_stride * 2;
+    corr = a.corr + (size_t)f * 2 * MPE_MAX_LEDS;
+    for (int e = gl; e < 12; e += G) S.T[e] = a.pose_io[(size_t)f * 16 + e];
+    for (int e = gl; e < 36; e += G) S.A0[e] = 0;
+  }
   const double fx = K[0], fy = K[4];
-
-  for (int e = gl; e < 12; e += G) S.T[e] = a.pose_io[(size_t)f * 16 + e];
-  for (int e = gl; e < 36; e += G) S.A0[e] = 0;
-  __syncwarp(gmask);
+  __syncwarp();
 
   int iters = 0;
+  bool done = false;
   for (int it = 0; it < 500; ++it) {                               // max_itr :738
+    const bool run = alive && !done;
+    if (!__any_sync(0xffffffffu, run)) break;
     double T[12], KT[12];
+    if (run) {
 #pragma unroll
-    for (int e = 0; e < 12; ++e) T[e] = S.T[e];
-    kt_product(K, T, KT);                                          // project2d :251-268 (same KT for every point)
-    // ---- 1. one correspondence per lane
-    for (int j = gl; j < k; j += G) {
-      const uint32_t led1 = corr[2 * j], det1 = corr[2 * j + 1];
-      S.used[j] = (det1 != 0);                                     // :761
-      if (det1 == 0) continue;
-      const int led = (int)led1 - 1, di = (int)det1 - 1;
-      const double ox = mk[3 * led], oy = mk[3 * led + 1], oz = mk[3 * led + 2];
-      double pu, pv;
-      kt_project(KT, ox, oy, oz, pu, pv);
-      const double e0 = det[2 * di] - pu, e1 = det[2 * di + 1] - pv;   // :769
-      // computeJacobian :932-960
-      const double x = T[0] * ox + T[1] * oy + T[2] * oz + T[3] * 1.0;
-      const double y = T[4] * ox + T[5] * oy + T[6] * oz + T[7] * 1.0;
-      const double z = T[8] * ox + T[9] * oy + T[10] * oz + T[11] * 1.0;
-      const double z_2 = z * z;
-      double* Jj = S.J[j];
-      Jj[0] = 1 / z * fx; Jj[1] = 0; Jj[2] = -x / z_2 * fx; Jj[3] = -x * y / z_2 * fx; Jj[4] = (1 + (x * x / z_2)) * fx; Jj[5] = -y / z * fx;
-      Jj[6] = 0; Jj[7] = 1 / z * fy; Jj[8] = -y / z_2 * fy; Jj[9] = -(1 + y * y / z_2) * fy; Jj[10] = x * y / z_2 * fy; Jj[11] = x / z * fy;
-      Jj[12] = e0; Jj[13] = e1;
-    }
-    __syncwarp(gmask);
-    // ---- 2. one entry of (A, b) per lane, contributions added in correspondence order
-    for (int e = gl; e < 27; e += G) {
-      double acc = 0;
-      if (e < 21) {
-        int r = 0, c = e;                                          // e -> (r, c), c <= r, rows of the lower triangle one after another
-        while (c > r) { c -= r + 1; ++r; }
-        for (int j = 0; j < k; ++j) {
-          if (!S.used[j]) continue;
-          const double* Jj = S.J[j];
-          acc += Jj[r] * Jj[c] + Jj[6 + r] * Jj[6 + c];
-        }
-        S.A0[r * 6 + c] = acc; S.A0[c * 6 + r] = acc;              // J0[r]*J0[c] == J0[c]*J0[r]: the reference's two entries are equal
-        S.Aw[r * 6 + c] = acc; S.Aw[c * 6 + r] = acc;
-      } else {
-        const int r = e - 21;
-        for (int j = 0; j < k; ++j) {
-          if (!S.used[j]) continue;
-          const double* Jj = S.J[j];
-          acc += Jj[r] * Jj[12] + Jj[6 + r] * Jj[13];
-        }
-        S.b[r] = acc;
+      for (int e = 0; e < 12; ++e) T[e] = S.T[e];
+      kt_product(K, T, KT);                                        // project2d :251-268 (same KT for every point)
+      // ---- 1. one correspondence per lane
+      for (int j = gl; j < k; j += G) {
+        const uint32_t led1 = corr[2 * j], det1 = corr[2 * j + 1];
+        S.used[j] = (det1 != 0);                                   // :761
+        if (det1 == 0) continue;
+        const int led = (int)led1 - 1, di = (int)det1 - 1;
+        const double ox = mk[3 * led], oy = mk[3 * led + 1], oz = mk[3 * led + 2];
+        double pu, pv;
+        kt_project(KT, ox, oy, oz, pu, pv);
+        const double e0 = det[2 * di] - pu, e1 = det[2 * di + 1] - pv;   // :769
+        // computeJacobian :932-960
+        const double x = T[0] * ox + T[1] * oy + T[2] * oz + T[3] * 1.0;
+        const double y = T[4] * ox + T[5] * oy + T[6] * oz + T[7] * 1.0;
+        const double z = T[8] * ox + T[9] * oy + T[10] * oz + T[11] * 1.0;
+        const double z_2 = z * z;
+        double* Jj = S.J[j];
+        Jj[0] = 1 / z * fx; Jj[1] = 0; Jj[2] = -x / z_2 * fx; Jj[3] = -x * y / z_2 * fx; Jj[4] = (1 + (x * x / z_2)) * fx; Jj[5] = -y / z * fx;
+        Jj[6] = 0; Jj[7] = 1 / z * fy; Jj[8] = -y / z_2 * fy; Jj[9] = -(1 + y * y / z_2) * fy; Jj[10] = x * y / z_2 * fy; Jj[11] = x / z * fy;
+        Jj[12] = e0; Jj[13] = e1;
       }
     }
-    __syncwarp(gmask);
+    __syncwarp();
+    // ---- 2. one entry of (A, b) per lane, contributions added in correspondence order
+    if (run) {
+      for (int e = gl; e < 27; e += G) {
+        double acc = 0;
+        if (e < 21) {
+          int r = 0, c = e;                                        // e -> (r, c), c <= r, rows of the lower triangle one after another
+          while (c > r) { c -= r + 1; ++r; }
+          for (int j = 0; j < k; ++j) {
+            if (!S.used[j]) continue;
+            const double* Jj = S.J[j];
+            acc += Jj[r] * Jj[c] + Jj[6 + r] * Jj[6 + c];
+          }
+          S.A0[r * 6 + c] = acc; S.A0[c * 6 + r] = acc;            // J0[r]*J0[c] == J0[c]*J0[r]: the reference's two entries are equal
+          S.Aw[r * 6 + c] = acc; S.Aw[c * 6 + r] = acc;
+        } else {
+          const int r = e - 21;
+          for (int j = 0; j < k; ++j) {
+            if (!S.used[j]) continue;
+            const double* Jj = S.J[j];
+            acc += Jj[r] * Jj[12] + Jj[6 + r] * Jj[13];
+          }
+          S.b[r] = acc;
+        }
+      }
+    }
+    __syncwarp();
     // ---- 3. dT = A.ldlt().solve(b)  (:778), arithmetic of ldlt_solve6
     uint32_t pk = 0x543210u;                                       // perm[i] = nibble i
 #pragma unroll
     for (int kk = 0; kk < 6; ++kk) {
-      int p = kk;
-      double best = fabs(S.Aw[nib(pk, kk) * 7]);
+      int pkk = 0;
+      double d = 1.0;
+      if (run) {
+        int p = kk;
+        double best = fabs(S.Aw[nib(pk, kk) * 7]);
 #pragma unroll
-      for (int i = kk + 1; i < 6; ++i) {
-        const double v = fabs(S.Aw[nib(pk, i) * 7]);
-        if (v > best) { best = v; p = i; }
+        for (int i = kk + 1; i < 6; ++i) {
+          const double v = fabs(S.Aw[nib(pk, i) * 7]);
+          if (v > best) { best = v; p = i; }
+        }
+        pk = nib_swap(pk, kk, p);
+        pkk = nib(pk, kk);
+        d = S.Aw[pkk * 7];
+        const int n_tr = 5 - kk, n_pairs = n_tr * (n_tr + 1) / 2;
+        for (int e = gl; e < n_pairs; e += G) {                     // Schur update of the trailing lower triangle (column kk still unscaled)
+          int io = 0, jo = e;
+          while (jo > io) { jo -= io + 1; ++io; }
+          const int pi = nib(pk, kk + 1 + io), pj = nib(pk, kk + 1 + jo);
+          const double v = S.Aw[pi * 6 + pj] - S.Aw[pi * 6 + pkk] * S.Aw[pj * 6 + pkk] / d;
+          S.Aw[pi * 6 + pj] = v; S.Aw[pj * 6 + pi] = v;
+        }
       }
-      pk = nib_swap(pk, kk, p);
-      const int pkk = nib(pk, kk);
-      const double d = S.Aw[pkk * 7];
-      const int n_tr = 5 - kk, n_pairs = n_tr * (n_tr + 1) / 2;
-      for (int e = gl; e < n_pairs; e += G) {                       // Schur update of the trailing lower triangle (column kk still unscaled)
-        int io = 0, jo = e;
-        while (jo > io) { jo -= io + 1; ++io; }
-        const int pi = nib(pk, kk + 1 + io), pj = nib(pk, kk + 1 + jo);
-        const double v = S.Aw[pi * 6 + pj] - S.Aw[pi * 6 + pkk] * S.Aw[pj * 6 + pkk] / d;
-        S.Aw[pi * 6 + pj] = v; S.Aw[pj * 6 + pi] = v;
-      }
-      __syncwarp(gmask);
-      for (int i = kk + 1 + gl; i < 6; i += G) { const int pi = nib(pk, i); S.Aw[pi * 6 + pkk] = S.Aw[pi * 6 + pkk] / d; }   // L(i,kk)
-      __syncwarp(gmask);
+      __syncwarp();
+      if (run)
+        for (int i = kk + 1 + gl; i < 6; i += G) { const int pi = nib(pk, i); S.Aw[pi * 6 + pkk] = S.Aw[pi * 6 + pkk] / d; }   // L(i,kk)
+      __syncwarp();
     }
-    double dT[6];
-    {
+    double dT[6] = {0, 0, 0, 0, 0, 0};
+    if (run) {
       double y[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) y[i] = S.b[nib(pk, i)];
@@ -865,13 +884,15 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
 #pragma unroll
         for (int i = 0; i < 6; ++i) S.dT[nib(pk, i)] = y[i];
       }
-      __syncwarp(gmask);
+    }
+    __syncwarp();
+    // ---- 4. T <- exp(dT) * T  (:781, :962-994), arithmetic of exp_map_left_multiply
+    double ux = 0, uy = 0, uz = 0;
+    if (run) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) dT[i] = S.dT[i];
-    }
-    // ---- 4. T <- exp(dT) * T  (:781, :962-994), arithmetic of exp_map_left_multiply
-    {
-      const double ux = dT[0], uy = dT[1], uz = dT[2], wx = dT[3], wy = dT[4], wz = dT[5];
+      ux = dT[0]; uy = dT[1]; uz = dT[2];
+      const double wx = dT[3], wy = dT[4], wz = dT[5];
       const double theta = sqrt(wx * wx + wy * wy + wz * wz);
       const double theta_squared = theta * theta;
       double sn = 0, cs = 0, kv1 = 0, kv2 = 0;
@@ -894,7 +915,9 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
         }
         S.rv[e] = r_ij; S.rv[9 + e] = v_ij;
       }
-      __syncwarp(gmask);
+    }
+    __syncwarp();
+    if (run) {
       for (int e = gl; e < 12; e += G) {
         const int i = e >> 2, j = e & 3;
         const double ti = S.rv[9 + 3 * i] * ux + S.rv[9 + 3 * i + 1] * uy + S.rv[9 + 3 * i + 2] * uz;
@@ -908,46 +931,59 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
         sacc += ti * bottom;
         S.T[e] = sacc;
       }
-      __syncwarp(gmask);
     }
-    ++iters;
-    double mx = -1;                                                 // norm_max :1073-1085
+    __syncwarp();
+    if (run) {
+      ++iters;
+      double mx = -1;                                               // norm_max :1073-1085
 #pragma unroll
-    for (int q = 0; q < 6; ++q) { const double av = fabs(dT[q]); if (av > mx) mx = av; }
-    if (mx <= 1e-13) break;                                         // :786
+      for (int q = 0; q < 6; ++q) { const double av = fabs(dT[q]); if (av > mx) mx = av; }
+      if (mx <= 1e-13) done = true;                                 // :786
+    }
   }
 
   // ---- covariance = A^-1 of the last iteration (:790), arithmetic of inverse6; the row exchanges are a permutation
-  for (int e = gl; e < 72; e += G) { const int i = e / 12, j = e - 12 * i; S.tab[e] = (j < 6) ? S.A0[i * 6 + j] : ((j - 6 == i) ? 1.0 : 0.0); }
-  __syncwarp(gmask);
+  if (alive)
+    for (int e = gl; e < 72; e += G) { const int i = e / 12, j = e - 12 * i; S.tab[e] = (j < 6) ? S.A0[i * 6 + j] : ((j - 6 == i) ? 1.0 : 0.0); }
+  __syncwarp();
   uint32_t rp = 0x543210u;
 #pragma unroll
   for (int kk = 0; kk < 6; ++kk) {
-    int p = kk;
-    double best = fabs(S.tab[nib(rp, kk) * 12 + kk]);
+    int rk = 0;
+    double pv = 1.0;
+    if (alive) {
+      int p = kk;
+      double best = fabs(S.tab[nib(rp, kk) * 12 + kk]);
 #pragma unroll
-    for (int i = kk + 1; i < 6; ++i) {
-      const double v = fabs(S.tab[nib(rp, i) * 12 + kk]);
-      if (v > best) { best = v; p = i; }
+      for (int i = kk + 1; i < 6; ++i) {
+        const double v = fabs(S.tab[nib(rp, i) * 12 + kk]);
+        if (v > best) { best = v; p = i; }
+      }
+      rp = nib_swap(rp, kk, p);
+      rk = nib(rp, kk);
+      pv = S.tab[rk * 12 + kk];
     }
-    rp = nib_swap(rp, kk, p);
-    const int rk = nib(rp, kk);
-    const double pv = S.tab[rk * 12 + kk];
-    __syncwarp(gmask);                                              // everybody has read the pivot before the row is scaled
-    for (int j = gl; j < 12; j += G) S.tab[rk * 12 + j] = S.tab[rk * 12 + j] / pv;
-    __syncwarp(gmask);
-    double fct[6];
+    __syncwarp();                                                   // everybody has read the pivot before the row is scaled
+    if (alive)
+      for (int j = gl; j < 12; j += G) S.tab[rk * 12 + j] = S.tab[rk * 12 + j] / pv;
+    __syncwarp();
+    double fct[6] = {0, 0, 0, 0, 0, 0};
+    if (alive) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) fct[i] = S.tab[nib(rp, i) * 12 + kk];
-    __syncwarp(gmask);                                              // factors read before column kk is overwritten
-    for (int e = gl; e < 72; e += G) {
-      const int i = e / 12, j = e - 12 * i;
-      if (i == kk) continue;
-      const double fi = (i == 0) ? fct[0] : (i == 1) ? fct[1] : (i == 2) ? fct[2] : (i == 3) ? fct[3] : (i == 4) ? fct[4] : fct[5];
-      if (fi != 0) { const int ri = nib(rp, i); S.tab[ri * 12 + j] = S.tab[ri * 12 + j] - fi * S.tab[rk * 12 + j]; }
+      for (int i = 0; i < 6; ++i) fct[i] = S.tab[nib(rp, i) * 12 + kk];
     }
-    __syncwarp(gmask);
+    __syncwarp();                                                   // factors read before column kk is overwritten
+    if (alive) {
+      for (int e = gl; e < 72; e += G) {
+        const int i = e / 12, j = e - 12 * i;
+        if (i == kk) continue;
+        const double fi = (i == 0) ? fct[0] : (i == 1) ? fct[1] : (i == 2) ? fct[2] : (i == 3) ? fct[3] : (i == 4) ? fct[4] : fct[5];
+        if (fi != 0) { const int ri = nib(rp, i); S.tab[ri * 12 + j] = S.tab[ri * 12 + j] - fi * S.tab[rk * 12 + j]; }
+      }
+    }
+    __syncwarp();
   }
+  if (!alive) return;
   if (a.cov)
     for (int e = gl; e < 36; e += G) { const int i = e / 6, j = e - 6 * i; a.cov[(size_t)f * 36 + e] = S.tab[nib(rp, i) * 12 + 6 + j]; }
   double* po = a.pose_io + (size_t)f * 16;

@@ -48,6 +48,8 @@ struct DevBuffers {
   uint4* hot_tiles = nullptr;      // [max_batch * flags_per_frame]
   uint16_t* pool = nullptr;        // [max_batch * kPoolPerFrame]
   uint32_t* counters = nullptr;    // [kLanes][2]  (one pair per concurrently running sub-batch)
+  uint32_t* tile_list = nullptr;   // [max_batch * flags_per_frame]  K1 work list of per-stream-ROI launches
+  uint32_t* tile_count = nullptr;  // [1]
   // tracking loop
   StreamState* streams = nullptr;  // [max_batch]
   Roi* result_rois = nullptr;      // [max_batch]
@@ -190,6 +192,7 @@ int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_
   if (g->n_ct > 1 && forced_tw <= 0) tw = kMaxTileWidthPx;
   g->tw_px = tw;
   g->frame_map = nullptr;
+  g->tile_list = nullptr; g->tile_count = nullptr;
   // widest span of u32 elements a tile can touch: it starts at the 16-pixel boundary at or below x - R (TMA needs a
   // 16-byte aligned innermost coordinate) and must reach pixel x + tw + R - 1
   int span = (tw + 2 * radius - 1 + 15) / 4 + 1;
@@ -239,6 +242,15 @@ int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, 
   a.g.n_frames = n;
   a.g.rois = rois_dev;
   a.g.frame_map = frame_map;
+  // per-frame ROIs: list the tiles the ROIs touch (the packed entry holds 20 bits of frame, 7 of strip, 5 of column tile)
+  const bool listed = rois_dev && a.g.n_strips <= 128 && a.g.n_ct <= 32 && n < (1 << 20);
+  if (listed) {
+    CUDA_TRY(c, cudaMemsetAsync(c->d.tile_count, 0, sizeof(uint32_t), st));
+    CUDA_TRY(c, launch_build_tile_list(a.g, c->d.tile_list, c->d.tile_count, st));
+    ++c->launches;
+    a.g.tile_list = c->d.tile_list;
+    a.g.tile_count = c->d.tile_count;
+  }
   CUtensorMap tmap;
   FrameSource sub = src;
   sub.base = src.base + (size_t)f0 * src.frame_stride;
@@ -508,6 +520,8 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.hot_tiles, B * c->flags_per_frame));
   CREATE_TRY(dev_alloc(&c->d.pool, B * kPoolPerFrame));
   CREATE_TRY(dev_alloc(&c->d.counters, 2 * kLanes));
+  CREATE_TRY(dev_alloc(&c->d.tile_list, B * c->flags_per_frame));
+  CREATE_TRY(dev_alloc(&c->d.tile_count, 1));
   CREATE_TRY(dev_alloc(&c->d.streams, B));
   CREATE_TRY(dev_alloc(&c->d.result_rois, B));
   CREATE_TRY(dev_alloc(&c->d.pred_px, B * MPE_MAX_LEDS * 2));
@@ -543,7 +557,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
   cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.combos); cudaFree(c->d.triples); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
-  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.tile_list); cudaFree(c->d.tile_count); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
   cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

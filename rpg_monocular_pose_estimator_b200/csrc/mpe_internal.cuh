@@ -58,6 +58,10 @@ struct K1Geom {
   int mask_rows;             // rows reserved per frame in the mask buffer
   int flags_per_frame;       // row-flag words reserved per frame
   const int* frame_map;      // optional [n_frames]: index of the image (z coordinate / frame_stride multiple) each entry reads
+  // per-frame-ROI launches: the tiles that intersect an ROI, listed by build_tile_list_kernel (f << 12 | strip << 5 | column tile),
+  // instead of walking the n_frames x n_strips x n_ct grid and testing every tile against its frame's ROI
+  const uint32_t* tile_list; // optional
+  const uint32_t* tile_count;
 };
 
 struct K1aArgs {
@@ -165,6 +169,7 @@ cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t
 cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st);
 cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st);
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
+cudaError_t launch_build_tile_list(const K1Geom& g, uint32_t* list, uint32_t* count, cudaStream_t st);
 cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st);
 cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st);
