@@ -471,7 +471,11 @@ static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, i
     configured = smem;
   }
   int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
-  int ctas_per_sm = (smem <= 110 * 1024) ? 2 : 1;
+  // CTAs per SM: two for the ~100 KB rings of whole-image rows; up to four (the register limit: 256 threads x 60 registers) for the
+  // small boxes of tracking-mode ROIs, whose loads are latency bound — more boxes in flight per SM
+  int ctas_per_sm = (int)((220 * 1024) / smem);
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
   int grid = n_tiles < n_sms * ctas_per_sm ? n_tiles : n_sms * ctas_per_sm;
   if (grid < 1) grid = 1;
   kern<<<grid, kK1Threads, smem, st>>>(tmap, a);

@@ -170,6 +170,16 @@ __device__ int decode_histogram(uint32_t* hist, int n_det, int n_obj, uint32_t t
   return n;
 }
 
+// frames that take part in this sweep (active and with enough detections), in any order
+__global__ void compact_active_kernel(const K2Args a) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.n_frames) return;
+  if (!a.active[f]) return;
+  const int n_det = a.n_det[f];
+  if (n_det < 4 || n_det > MPE_MAX_DET) return;
+  a.frame_list[atomicAdd(a.frame_count, 1u)] = f;
+}
+
 // Exact scoring of one finite pose hypothesis H = [R|C] (camera -> world), exactly as PoseEstimator::initialise does it
 // (pose_estimator.cpp:656-697): general inverse, project2d of the unused LEDs, nearest back-projection for every unused
 // detection, votes.  ids packs d0,d1,d2,o0,o1,o2 (4 bits each).  Not inlined: it runs for ~1 % of the hypotheses.
@@ -291,17 +301,24 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
   if (tid < 2) q_n[tid] = 0;
   __syncthreads();
   const double* __restrict__ tt = a.triples;
-  const int n_units = a.n_frames * a.split;
+  // units = (frame, part).  With a compacted frame list the number of parts adapts to the length of the list, so that a
+  // handful of re-initialising streams still spreads over the grid.
+  const bool listed = a.frame_list != nullptr;
+  const int n_listed = listed ? (int)*a.frame_count : a.n_frames;
+  int split = a.split;
+  if (listed && n_listed > 0) { const int s2 = (int)gridDim.x / n_listed; split = max(split, min(16, s2)); }
+  const int n_units = n_listed * split;
   int rot = 0;                                          // flat position (mod blockDim) where this unit's first problem falls
   int par = 0;                                          // which of the two queue counters is being filled
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int f = unit / a.split, part = unit - f * a.split;
-    if (a.active && !a.active[f]) continue;
+    const int fi = unit / split, part = unit - fi * split;
+    const int f = listed ? a.frame_list[fi] : fi;
+    if (!listed && a.active && !a.active[f]) continue;
     const int n_det = a.n_det[f];
     if (n_det < 4 || n_det > MPE_MAX_DET) continue;     // pose_estimator.cpp:80 (min_num_leds_detected_ = 4); flagged by decode_kernel
     const int n_comb = n_det * (n_det - 1) * (n_det - 2) / 6;
     const int total = n_comb * n_perm;
-    const int chunk = (total + a.split - 1) / a.split;
+    const int chunk = (total + split - 1) / split;
     const int t_begin = part * chunk, t_end = min(total, t_begin + chunk);
     const int count = max(t_end - t_begin, 0);
     const double* det = a.det + (size_t)f * a.det_stride * 2;
@@ -421,6 +438,12 @@ cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st) {
   // default: one CTA per (frame, part) — measured faster than fewer persistent CTAs (hardware CTA scheduling balances the
   // tail); MPE_K2_GRID_MULT overrides for experiments
   int grid = (mult == 0) ? n_units : n_sms * MPE_K2_MINBLOCKS * mult;
+  if (a.frame_list) {                                     // masked sweep (tracking step): compact the frames that take part, persistent CTAs walk the list
+    compact_active_kernel<<<(a.n_frames + 255) / 256, 256, 0, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    grid = n_sms * MPE_K2_MINBLOCKS * 2;
+  }
   if (grid > n_units) grid = n_units;
   // block size: 256 threads (measured best for 600 and 18 816 problems per frame: the kernel is latency bound, a fuller last
   // pass with 160 threads and five CTAs per SM was 3 % slower); units with fewer problems than that get a CTA of their size

@@ -285,6 +285,12 @@ __global__ void __launch_bounds__(kK3aThreads) check_kernel(const K3Args a, int 
   const double* K = a.cam.K;
   const double* mk = a.pp.markers;
 
+  // ---- a CTA none of whose frames takes part leaves at once (masked passes of the tracking step: ~0.5 % of the streams re-initialise)
+  {
+    const int fq = f0 + tid;
+    const int takes_part = (tid < G) && (fq < a.n_frames) && !(a.active && !a.active[fq]);
+    if (!__syncthreads_or(takes_part)) return;
+  }
   // ---- stage the frames of this CTA
   if (tid < G) {
     int f = f0 + tid;

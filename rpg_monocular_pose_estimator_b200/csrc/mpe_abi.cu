@@ -50,6 +50,8 @@ struct DevBuffers {
   uint32_t* counters = nullptr;    // [kLanes][2]  (one pair per concurrently running sub-batch)
   uint32_t* tile_list = nullptr;   // [max_batch * flags_per_frame]  K1 work list of per-stream-ROI launches
   uint32_t* tile_count = nullptr;  // [1]
+  int* k2_list = nullptr;          // [max_batch]  frames taking part in a masked K2 sweep
+  uint32_t* k2_count = nullptr;    // [1]
   // tracking loop
   StreamState* streams = nullptr;  // [max_batch]
   Roi* result_rois = nullptr;      // [max_batch]
@@ -339,6 +341,12 @@ int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* acti
   k.n_corr = c->d.n_corr + slot0;
   k.frame_flags = c->d.flags + slot0;
   k.active = active;
+  if (active) {
+    k.frame_list = c->d.k2_list;
+    k.frame_count = c->d.k2_count;
+    CUDA_TRY(c, cudaMemsetAsync(k.frame_count, 0, sizeof(uint32_t), st));
+    ++c->launches;                                     // compact_active_kernel
+  }
   CUDA_TRY(c, cudaMemsetAsync(k.hist, 0, (size_t)n * MPE_MAX_DET * MPE_MAX_LEDS * sizeof(uint32_t), st));
   time_begin(c, 2, st);
   CUDA_TRY(c, launch_p3p_sweep(k, c->n_sms, st));
@@ -522,6 +530,8 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.counters, 2 * kLanes));
   CREATE_TRY(dev_alloc(&c->d.tile_list, B * c->flags_per_frame));
   CREATE_TRY(dev_alloc(&c->d.tile_count, 1));
+  CREATE_TRY(dev_alloc(&c->d.k2_list, B));
+  CREATE_TRY(dev_alloc(&c->d.k2_count, 1));
   CREATE_TRY(dev_alloc(&c->d.streams, B));
   CREATE_TRY(dev_alloc(&c->d.result_rois, B));
   CREATE_TRY(dev_alloc(&c->d.pred_px, B * MPE_MAX_LEDS * 2));
@@ -557,7 +567,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.frames); cudaFree(c->d.rowflags); cudaFree(c->d.mask); cudaFree(c->d.n_det); cudaFree(c->d.flags);
   cudaFree(c->d.det); cudaFree(c->d.centers); cudaFree(c->d.hist); cudaFree(c->d.combos); cudaFree(c->d.triples); cudaFree(c->d.corr);
   cudaFree(c->d.n_corr); cudaFree(c->d.pose); cudaFree(c->d.cov); cudaFree(c->d.ok); cudaFree(c->d.iters);
-  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.tile_list); cudaFree(c->d.tile_count); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
+  cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.tile_list); cudaFree(c->d.tile_count); cudaFree(c->d.k2_list); cudaFree(c->d.k2_count); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
   cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

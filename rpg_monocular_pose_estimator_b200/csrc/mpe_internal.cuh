@@ -113,6 +113,10 @@ struct K2Args {
   int* n_corr;               // [n_frames]
   int* frame_flags;          // [n_frames] in/out
   const uint8_t* active;     // optional [n_frames]: run the sweep only where nonzero
+  // with `active`: the frames that take part, compacted by compact_active_kernel, so that the sweep's CTAs walk a short list
+  // instead of 8192 CTAs finding out one by one that their frame is idle (tracking steps re-initialise ~0.5 % of the streams)
+  int* frame_list;           // [n_frames]
+  uint32_t* frame_count;     // [1]
 };
 
 struct K3Args {
