@@ -303,7 +303,16 @@ __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_consta
 // K1c — blur_kernel: exact threshold + fixed-point Gaussian on the hot tiles only, reading the few source pixels it
 // needs straight from global memory (about 1 % of the frame bytes), and writing the 1-bit foreground rows + row flags.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurThreads = 128;
+// a hot tile offers only ~50-100 work items and six block barriers: small CTAs, many per SM (measured @8192 frames: 128 threads x 8
+// CTAs/SM 0.203 ms, 64 x 16 0.179 ms, 32 x 24 0.257 ms)
+#ifndef MPE_BLUR_THREADS
+#define MPE_BLUR_THREADS 64
+#endif
+#ifndef MPE_BLUR_CTAS_PER_SM
+#define MPE_BLUR_CTAS_PER_SM 16
+#endif
+constexpr int kBlurThreads = MPE_BLUR_THREADS;
+constexpr int kBlurWarps = kBlurThreads / 32;
 
 __device__ __forceinline__ int blur_smem_words(int box_w, int tw_px) {
   return 4 + kTileRows * ((box_w + 31) >> 5) + kTileRows * ((tw_px + 31) >> 5);
@@ -440,7 +449,9 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
       misc[1] = 0u; misc[2] = 0u;
     }
     const int words_per_ct = g.tw_px >> 5;   // only used when n_ct > 1 (tw_px is a multiple of 32 then)
-    uint32_t rm = rowmask & (0x11111111u << warp);                     // 4 warps: warp w copies rows r with (r & 3) == w
+    // warp w copies the rows r with r % kBlurWarps == w
+    constexpr uint32_t kRowsOfWarp0 = (kBlurWarps == 1) ? 0xffffffffu : (kBlurWarps == 2) ? 0x55555555u : (kBlurWarps == 4) ? 0x11111111u : 0x01010101u;
+    uint32_t rm = rowmask & (kRowsOfWarp0 << warp);
     while (rm) {
       const int r = __ffs(rm) - 1;
       rm &= rm - 1;
@@ -496,7 +507,10 @@ template <int RT>
 static cudaError_t launch_blur_r(const K1aArgs& a, int n_sms, cudaStream_t st) {
   size_t bsmem = (size_t)(4 + kTileRows * ((a.g.box_w + 31) >> 5) + kTileRows * ((a.g.tw_px + 31) >> 5)) * 4 + (size_t)kTileRows * a.g.box_w * 2;
   int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
-  int grid = n_tiles < n_sms * 8 ? n_tiles : n_sms * 8;
+  int per_sm = MPE_BLUR_CTAS_PER_SM;
+  if ((size_t)per_sm * (bsmem + 1024) > 220 * 1024) per_sm = (int)((220 * 1024) / (bsmem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  int grid = n_tiles < n_sms * per_sm ? n_tiles : n_sms * per_sm;
   blur_kernel<RT><<<grid, kBlurThreads, bsmem, st>>>(a);
   return cudaGetLastError();
 }

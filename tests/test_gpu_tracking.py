@@ -198,3 +198,33 @@ def test_zero_copy_ingest_reads_pinned_images_in_place(gpu_ctx_752):
     ctx.set_ingest_mode(ctx.INGEST_AUTO)
     r = results_to_arrays(ctx.streams_step(pageable, times[0]))
     assert r["updated"].sum() == S
+
+
+def test_streams_1080p_match_oracle():
+    """Tracking at 1920x1080 (34 strips x 8 column tiles per frame in the K1 tile work list, ROIs that straddle column tiles)."""
+    import torch
+    import rpg_monocular_pose_estimator_b200 as mpe
+    T, S = 8, 3
+    streams = [synth.make_stream_scene(T, n_leds=5, width=1920, height=1080, seed=4100 + s) for s in range(S)]
+    ctx = mpe.Context(0, S, 1920, 1080)
+    try:
+        out = _run(streams, ctx, torch)
+        n_upd = 0
+        for s, sc in enumerate(streams):
+            est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+            for t in range(T):
+                upd = est.estimate_body_pose(sc.frames[t], sc.times[t])
+                r = out[t][s]
+                assert bool(r["updated"]) == upd, (s, t)
+                assert tuple(r["roi"]) == tuple(est.region_of_interest), (s, t)
+                if upd:
+                    n_upd += 1
+                    k = r["n_corr"]
+                    assert np.array_equal(r["corr"][:2 * k].reshape(k, 2), est.correspondences()), (s, t)
+                    dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+                    assert dt < 1e-6 and dr < 1e-6, (s, t, dt, dr)
+                    assert r["gn_iters"] == est.gn_iterations(), (s, t)
+        assert n_upd >= S * T - 3
+        assert out[-1]["roi"][:, 2].max() < 1920       # tracking inside ROIs
+    finally:
+        ctx.close()
