@@ -755,7 +755,9 @@ __device__ __forceinline__ void undistort_point(const DevCamera& cam, float sx, 
 }
 
 constexpr int kBlobWarpsPerCta = 4;
-constexpr int kMaxFlagWords = 160;     // row-flag words cached per frame (>= ceil(H/32) * n_ct; 2160-row images with 2 column tiles fit)
+// kMaxFlagWords (mpe_internal.cuh): row-flag words cached per frame, >= n_strips * n_ct of the launch (the host rejects larger
+// geometries).  1080p with the 256-px tracking tiles needs 34 x 8 = 272; the first limit of 160 was found by the 1080p tracking test:
+// out-of-range flag words fed the border follower garbage and its step limit of 4*w*h turned that into a hang.
 constexpr int kMaxRowsListed = 2176;
 
 struct WarpScratch {

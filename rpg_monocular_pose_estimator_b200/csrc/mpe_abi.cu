@@ -204,6 +204,7 @@ int make_geometry(mpe_ctx* c, int w, int h, Roi roi, int max_roi_w, int max_roi_
   g->mask_rows = c->max_h;
   g->flags_per_frame = c->flags_per_frame;
   if (g->n_strips * g->n_ct > g->flags_per_frame) return MPE_E_CAPACITY;
+  if (g->n_strips * g->n_ct > kMaxFlagWords) return MPE_E_CAPACITY;      // K1b's per-frame cache of row flags
   if (g->n_ct * ((tw + 31) / 32) > g->mask_wpr && g->n_ct > 1) return MPE_E_CAPACITY;
   return MPE_OK;
 }

@@ -14,6 +14,7 @@ constexpr int kMaxTaps = 2 * kMaxRadius + 1;
 constexpr int kMaxTileWidthPx = 960; // column-tile width limit (TMA box <= 256 u32 elements incl. halo)
 constexpr int kK1Threads = 256;
 constexpr int kCandCap = 256;        // candidate contour starts buffered per frame-warp in K1b
+constexpr int kMaxFlagWords = 512;   // row-flag words (strips x column tiles) K1b caches per frame; larger geometries are rejected
 constexpr int kMaxCombos = MPE_MAX_DET * (MPE_MAX_DET - 1) * (MPE_MAX_DET - 2) / 6;   // 3-subsets of the detections (560)
 constexpr int kMaxPerms = MPE_MAX_LEDS * (MPE_MAX_LEDS - 1) * (MPE_MAX_LEDS - 2);     // ordered LED triples (3360)
 constexpr int kComboFields = 13;     // K2 detection-triple record (doubles)
