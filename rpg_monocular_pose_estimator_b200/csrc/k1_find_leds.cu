@@ -758,8 +758,9 @@ constexpr int kBlobWarpsPerCta = 4;
 // kMaxFlagWords (mpe_internal.cuh): row-flag words cached per frame, >= n_strips * n_ct of the launch (the host rejects larger
 // geometries).  1080p with the 256-px tracking tiles needs 34 x 8 = 272; the first limit of 160 was found by the 1080p tracking test:
 // out-of-range flag words fed the border follower garbage and its step limit of 4*w*h turned that into a hang.
-constexpr int kMaxRowsListed = 2176;
 
+// Per-warp scratch.  The two variable parts are sized per launch (row flags: strips x column tiles of the geometry; row list: image
+// rows), so that small images keep the footprint small and more frame-warps share an SM.
 struct WarpScratch {
   int cand_x[kCandCap];
   int cand_y[kCandCap];
@@ -770,9 +771,15 @@ struct WarpScratch {
   int kept_key[MPE_MAX_BLOBS];     // raster index of the contour start (sort key)
   float kept_cx[MPE_MAX_BLOBS];
   float kept_cy[MPE_MAX_BLOBS];
-  uint32_t rowflags[kMaxFlagWords];
-  uint16_t rows[kMaxRowsListed];   // rows of this frame that contain foreground
+  uint32_t* rowflags;              // [flags_cap]
+  uint16_t* rows;                  // [rows_cap] rows of this frame that contain foreground
+  int flags_cap, rows_cap;
 };
+
+__host__ __device__ inline size_t k1b_scratch_stride(int flags_cap, int rows_cap) {
+  size_t n = sizeof(WarpScratch) + (size_t)flags_cap * 4 + (size_t)rows_cap * 2;
+  return (n + 15) & ~(size_t)15;
+}
 
 __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane) {
   __syncwarp();
@@ -823,15 +830,27 @@ __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Ro
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(const K1bArgs a) {
+// latency bound (dependent mask loads while following a border): occupancy pays.  Eight CTAs per SM = 64 registers per thread and
+// a per-launch sized scratch; measured @8192 frames: 103 registers / 4 CTAs 0.271 ms, 80 / 6 0.220 ms, 64 / 8 0.195 ms
+#ifndef MPE_K1B_MINBLOCKS
+#define MPE_K1B_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extract_blobs_kernel(const K1bArgs a) {
   extern __shared__ __align__(16) uint8_t k1b_smem[];
-  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(k1b_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kBlobWarpsPerCta + warp;
   if (f >= a.g.n_frames) return;
   if (a.active && !a.active[f]) return;
-  WarpScratch& ws = scratch[warp];
   const K1Geom& g = a.g;
+  const int flags_cap = min(g.flags_per_frame, kMaxFlagWords), rows_cap = g.mask_rows;
+  uint8_t* my = k1b_smem + (size_t)warp * k1b_scratch_stride(flags_cap, rows_cap);
+  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(my);
+  if (lane == 0) {
+    ws.rowflags = reinterpret_cast<uint32_t*>(my + sizeof(WarpScratch));
+    ws.rows = reinterpret_cast<uint16_t*>(my + sizeof(WarpScratch) + (size_t)flags_cap * 4);
+    ws.flags_cap = flags_cap; ws.rows_cap = rows_cap;
+  }
+  __syncwarp();
   const Roi roi = g.rois ? g.rois[f] : g.roi;
   const int roi_wpr = (roi.w + 31) >> 5;
   const int roi_n_ct = (roi.w + g.tw_px - 1) / g.tw_px;
@@ -841,7 +860,7 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
   if (lane == 0) { ws.n_cand = 0; ws.n_kept = 0; ws.flags = 0; ws.n_rows = 0; }
   __syncwarp();
   const uint32_t* gflags = a.rowflags + (size_t)f * g.flags_per_frame;
-  for (int i = lane; i < roi_strips * g.n_ct && i < kMaxFlagWords; i += 32) ws.rowflags[i] = gflags[i];
+  for (int i = lane; i < roi_strips * g.n_ct && i < flags_cap; i += 32) ws.rowflags[i] = gflags[i];
   __syncwarp();
   for (int s = lane; s < roi_strips; s += 32) {
     uint32_t fl = 0;
@@ -850,7 +869,7 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
       int r = __ffs(fl) - 1;
       fl &= fl - 1;
       int slot = atomicAdd(&ws.n_rows, 1);
-      if (slot < kMaxRowsListed) ws.rows[slot] = (uint16_t)(s * kTileRows + r);
+      if (slot < rows_cap) ws.rows[slot] = (uint16_t)(s * kTileRows + r);
     }
   }
   __syncwarp();
@@ -866,7 +885,7 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
   m.words_per_ct = g.tw_px >> 5;
 
   // ---- contour-start candidates: one lane per foreground row, then lane-parallel border following
-  const int n_rows = min(ws.n_rows, kMaxRowsListed);
+  const int n_rows = min(ws.n_rows, rows_cap);
   for (int base = 0; base < n_rows; base += 32) {
     if (base + lane < n_rows) {
       const int y = ws.rows[base + lane];
@@ -914,12 +933,13 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta) extract_blobs_kernel(co
 
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
   int grid = (a.g.n_frames + kBlobWarpsPerCta - 1) / kBlobWarpsPerCta;
-  static bool configured = false;
-  size_t smem = sizeof(WarpScratch) * kBlobWarpsPerCta;
-  if (!configured) {
+  static size_t configured = 0;
+  const int flags_cap = a.g.flags_per_frame < kMaxFlagWords ? a.g.flags_per_frame : kMaxFlagWords;
+  size_t smem = k1b_scratch_stride(flags_cap, a.g.mask_rows) * kBlobWarpsPerCta;
+  if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(extract_blobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = smem;
   }
   extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, smem, st>>>(a);
   return cudaGetLastError();
