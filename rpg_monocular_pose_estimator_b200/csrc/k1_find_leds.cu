@@ -24,6 +24,7 @@
 // the memory roofline.  Only words whose neighbourhood is "hot" run the exact fixed-point arithmetic, and
 // its result is identical to the dense evaluation.
 #include "mpe_internal.cuh"
+#include <cstdlib>
 
 namespace mpe {
 
@@ -494,12 +495,23 @@ static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, i
 }
 
 static cudaError_t launch_scan(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
-  // ring depth: as many stages as fit in ~110 KB so that two CTAs share an SM
+  // Ring depth.  Per tile a CTA runs a latency chain (mbarrier wait -> shared-memory reads -> block barrier), so what hides latency
+  // is CTAs per SM, not a deeper ring: measured @8192 x 752x480: 2 CTAs x 3 stages 0.521 ms (0.87 of the HBM peak), 3 CTAs x 2
+  // stages 0.466 ms (0.97), 1 CTA x 4 stages 0.939 ms.  Rule: the depth (>= 2) that lets the most CTAs share an SM (at most four:
+  // 256 threads x 60 registers), ties to the deeper ring.  MPE_SCAN_STAGES=2|3|4 forces a depth.
   const int R = a.radius;
-  size_t s4 = find_leds_smem_bytes(a.g, R, 4), s3 = find_leds_smem_bytes(a.g, R, 3);
   bool low = a.threshold < 128;
-  if (s4 <= 110 * 1024) return low ? launch_scan_inst<true, 4>(a, tmap, n_sms, st) : launch_scan_inst<false, 4>(a, tmap, n_sms, st);
-  if (s3 <= 110 * 1024) return low ? launch_scan_inst<true, 3>(a, tmap, n_sms, st) : launch_scan_inst<false, 3>(a, tmap, n_sms, st);
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MPE_SCAN_STAGES"); forced = e ? atoi(e) : 0; }
+  int stages = 2, best_ctas = 0;
+  for (int sdepth = 2; sdepth <= 4; ++sdepth) {
+    int ctas = (int)((220 * 1024) / find_leds_smem_bytes(a.g, R, sdepth));
+    if (ctas > 4) ctas = 4;
+    if (ctas >= best_ctas && ctas >= 1) { best_ctas = ctas; stages = sdepth; }
+  }
+  if (forced >= 2 && forced <= 4) stages = forced;
+  if (stages == 4) return low ? launch_scan_inst<true, 4>(a, tmap, n_sms, st) : launch_scan_inst<false, 4>(a, tmap, n_sms, st);
+  if (stages == 3) return low ? launch_scan_inst<true, 3>(a, tmap, n_sms, st) : launch_scan_inst<false, 3>(a, tmap, n_sms, st);
   return low ? launch_scan_inst<true, 2>(a, tmap, n_sms, st) : launch_scan_inst<false, 2>(a, tmap, n_sms, st);
 }
 
