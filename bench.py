@@ -582,6 +582,7 @@ def main():
         ms_e2e = float(t.item()) / steps_e2e
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                "d2h_bytes_per_step": B * rec_bytes, "ms_per_step": ms_e2e, "steps": steps_e2e,
+               "h2d_gbs": B * W * H / (ms_e2e * 1e-3) / 1e9,      # PCIe-bound: compare with the box's pinned H2D copy rate (55.6 GB/s measured, tests/probes/pcie_probe.py)
                "api": "mpe_estimate_batch (pinned host frames -> host mpe_result records)"}
         assert int(results_to_arrays(r)["updated"].sum()) == n_updated
 
