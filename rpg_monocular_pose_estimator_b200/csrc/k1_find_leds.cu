@@ -1,13 +1,17 @@
 // K1 — LEDDetector::findLeds on the GPU (reference: monocular_pose_estimator_lib/src/led_detector.cpp:35-112).
 //
-//   find_leds_kernel   (K1a)  threshold-to-zero + 8-bit fixed-point Gaussian + "blurred != 0" mask, fused.
-//                             HBM-bound: every ROI byte is read exactly once from DRAM through TMA
-//                             (cp.async.bulk.tensor) into a multi-stage shared-memory ring; nothing but a
-//                             sparse 1-bit mask (rows that contain foreground) and one flag word per tile
-//                             is written back.
+//   scan_kernel          (K1a) the streaming pass.  HBM-bound: every ROI byte is read exactly once from DRAM through
+//                             TMA (cp.async.bulk.tensor) into a shared-memory ring and only asked "does this word hold
+//                             a byte above the threshold"; the few hot words go to a pool, nothing else is written.
+//                             Whole-image batches walk the frames x strips x column-tiles grid, per-frame ROIs (tracking)
+//                             a tile work list built by build_tile_list_kernel.
+//   blur_kernel          (K1c) exact THRESH_TOZERO + 8-bit fixed-point Gaussian + "blurred != 0" on the neighbourhood of
+//                             the hot words only; writes a sparse 1-bit mask (rows that contain foreground) and one
+//                             flag word per tile.
 //   extract_blobs_kernel (K1b) external contours (cv::findContours RETR_EXTERNAL / CHAIN_APPROX_NONE),
 //                             contourArea / boundingRect / moments, the four shape filters and
 //                             cv::undistortPoints, one warp per frame working on the sparse mask.
+//   (The first version fused K1a and K1c; see DESIGN.md section 4, decision 2, for why they are separate kernels.)
 //
 // Bit-exact contract (pinned against cv2 4.13):
 //   blur    taps = getGaussianKernelBitExact -> 8.8 fixed point (sum 256), horizontal pass 8.8, vertical

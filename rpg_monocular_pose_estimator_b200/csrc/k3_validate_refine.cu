@@ -12,6 +12,11 @@
 //                  accumulation in correspondence order, pivoted LDL^T, exponential map, covariance = A^-1.
 // (The first version used one warp per frame with lanes = subsets / correspondences and shuffle reductions; 31/32 of
 //  the issue slots of the sequential parts were wasted: 150 ns/frame against ~15 for this layout.)
+// Small batches (<= kGnCooperativeMaxFrames frames, e.g. one camera) are the opposite regime: the duration of a kernel is one
+// thread's dependent chain, so they get lane-cooperative kernels with the same arithmetic per value:
+//   check_wide_kernel    CTA per frame, warp = P3P solution, lane = subset;
+//   gauss_newton_kernel  32 lanes per frame: lane = correspondence for the Jacobians, lane = entry of the normal equations,
+//                        lane-parallel pivoted LDL^T and Gauss-Jordan (one frame: 105 -> 37 us).
 // FP64 / latency bound; reads < 1 KB per frame.  Compiled with -fmad=false.
 #include "mpe_internal.cuh"
 #include "p3p_device.cuh"
