@@ -513,7 +513,8 @@ static cudaError_t launch_scan(const K1aArgs& a, const CUtensorMap& tmap, int n_
     if (ctas > 4) ctas = 4;
     if (ctas >= best_ctas && ctas >= 1) { best_ctas = ctas; stages = sdepth; }
   }
-  if (forced >= 2 && forced <= 4) stages = forced;
+  if (forced >= 1 && forced <= 4) stages = forced;
+  if (stages == 1) return low ? launch_scan_inst<true, 1>(a, tmap, n_sms, st) : launch_scan_inst<false, 1>(a, tmap, n_sms, st);
   if (stages == 4) return low ? launch_scan_inst<true, 4>(a, tmap, n_sms, st) : launch_scan_inst<false, 4>(a, tmap, n_sms, st);
   if (stages == 3) return low ? launch_scan_inst<true, 3>(a, tmap, n_sms, st) : launch_scan_inst<false, 3>(a, tmap, n_sms, st);
   return low ? launch_scan_inst<true, 2>(a, tmap, n_sms, st) : launch_scan_inst<false, 2>(a, tmap, n_sms, st);
