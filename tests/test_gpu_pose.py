@@ -221,3 +221,41 @@ def test_sweep_reject_filter_never_changes_a_vote(gpu_ctx_752):
     finally:
         ctx.set_k2_filter(True)
     assert n_cases >= 70 and n_votes > 1000
+
+
+def test_large_batch_kernels_match_oracle():
+    """Batches above 1024 frames take the throughput kernels (thread per subset / thread per frame, CTA per frame in the sweep),
+    smaller ones the lane-cooperative kernels; both must give the oracle's results.  64 distinct frames replicated to 1280:
+    every replica equals its original bit for bit, and the originals equal the oracle."""
+    import rpg_monocular_pose_estimator_b200 as mpe
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    n_distinct, rep = 64, 20
+    sc = synth.make_cold_scene(n_distinct, n_leds=5, seed=8800)
+    frames = np.ascontiguousarray(np.tile(sc.frames, (rep, 1, 1)))
+    ctx = mpe.Context(0, n_distinct * rep, sc.width, sc.height)
+    try:
+        _config(ctx, sc)
+        big = results_to_arrays(ctx.estimate_batch(frames)).copy()           # 1280 frames: large-batch kernels
+        small = results_to_arrays(ctx.estimate_batch(sc.frames)).copy()      # 64 frames: cooperative kernels
+    finally:
+        ctx.close()
+    for r in range(rep):
+        assert big[r * n_distinct:(r + 1) * n_distinct].tobytes() == big[:n_distinct].tobytes(), r
+    n_upd = 0
+    for f in range(n_distinct):
+        est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+        upd = est.estimate_body_pose(sc.frames[f], sc.times[f])
+        for r in (big[f], small[f]):
+            assert bool(r["updated"]) == upd, f
+            if upd:
+                k = r["n_corr"]
+                assert np.array_equal(r["corr"][:2 * k].reshape(k, 2), est.correspondences()), f
+                dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+                assert dt < POS_TOL and dr < ROT_TOL, (f, dt, dr)
+                assert r["gn_iters"] == est.gn_iterations(), f
+        n_upd += int(upd)
+        # the two kernel families agree with each other far below the tolerance (same arithmetic per value)
+        if upd:
+            assert np.array_equal(big[f]["corr"], small[f]["corr"])
+            assert np.abs(big[f]["pose"] - small[f]["pose"]).max() < 1e-12, f
+    assert n_upd >= 0.85 * n_distinct
