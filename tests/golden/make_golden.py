@@ -37,3 +37,22 @@ for i in range(64):
     F.append(f.T); P.append(pts.T); S.append(sol); R.append(rc)
 np.savez_compressed(os.path.join(out, "p3p_kat.npz"), f=np.array(F), P=np.array(P), sol=np.array(S), rc=np.array(R))
 print("golden written")
+
+# Tracking sequences (estimateBodyPose frame by frame: cold start, ROI tracking, a whole-image retry after two blank frames)
+def tracking_golden(seed, n_frames=24, blank=(9, 10)):
+    sc = synth.make_stream_scene(n_frames, n_leds=5, seed=seed)
+    for b in blank:
+        sc.frames[b][:] = 0
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    upd, roi, ncorr, corr, pose, iters, ndet = [], [], [], [], [], [], []
+    for f in range(n_frames):
+        u = est.estimate_body_pose(sc.frames[f], sc.times[f])
+        upd.append(u); roi.append(est.region_of_interest); ndet.append(est.n_det)
+        c_ = est.correspondences() if u else np.zeros((0, 2), np.uint32)
+        cpad = np.zeros((5, 2), np.uint32); cpad[:len(c_)] = c_
+        corr.append(cpad); ncorr.append(len(c_)); pose.append(est.predicted_pose()); iters.append(est.gn_iterations() if u else 0)
+    return dict(seed=seed, blank=np.array(blank), updated=np.array(upd), roi=np.array(roi), n_det=np.array(ndet), n_corr=np.array(ncorr), corr=np.array(corr),
+                pose=np.array(pose), iters=np.array(iters))
+
+np.savez_compressed(os.path.join(out, "tracking_5leds.npz"), **tracking_golden(34))
+print("tracking golden written")

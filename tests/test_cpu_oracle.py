@@ -18,6 +18,34 @@ from tests.helpers import oracle_find_leds, pose_error, random_blob_image
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def _golden_tracking_scene():
+    g = np.load(os.path.join(GOLD, "tracking_5leds.npz"))
+    sc = synth.make_stream_scene(len(g["updated"]), n_leds=5, seed=int(g["seed"]))
+    for b in g["blank"]:
+        sc.frames[int(b)][:] = 0
+    return g, sc
+
+
+def test_oracle_reproduces_golden_tracking_sequence():
+    """estimateBodyPose frame by frame (cold start, ROI tracking with predictPose / determineROI / findCorrespondences, two blank
+    frames with whole-image retries) against the committed fixture: flags, ROIs, correspondences and iteration counts exactly,
+    poses to 1e-9."""
+    g, sc = _golden_tracking_scene()
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    for f in range(len(g["updated"])):
+        upd = est.estimate_body_pose(sc.frames[f], sc.times[f])
+        assert upd == bool(g["updated"][f]), f
+        assert tuple(est.region_of_interest) == tuple(g["roi"][f]), f
+        assert est.n_det == g["n_det"][f], f
+        if upd:
+            k = int(g["n_corr"][f])
+            assert np.array_equal(est.correspondences(), g["corr"][f][:k]), f
+            assert est.gn_iterations() == g["iters"][f], f
+            dt, dr = pose_error(est.predicted_pose(), g["pose"][f])
+            assert dt < 1e-9 and dr < 1e-9, (f, dt, dr)
+    assert g["updated"].sum() == len(g["updated"]) - 2 and g["roi"][1][2] < 752
+
+
 @pytest.mark.parametrize("n_leds,seed", [(4, 31), (5, 32), (8, 33)])
 def test_oracle_reproduces_golden(n_leds, seed):
     g = np.load(os.path.join(GOLD, f"cold_{n_leds}leds.npz"))

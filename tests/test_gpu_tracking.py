@@ -228,3 +228,26 @@ def test_streams_1080p_match_oracle():
         assert out[-1]["roi"][:, 2].max() < 1920       # tracking inside ROIs
     finally:
         ctx.close()
+
+
+def test_device_loop_matches_golden_tracking_fixture(gpu_ctx_752):
+    """The device-resident loop against the committed golden fixture directly (no oracle in the loop): tests/golden/tracking_5leds.npz."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tracking_5leds.npz"))
+    sc = synth.make_stream_scene(len(g["updated"]), n_leds=5, seed=int(g["seed"]))
+    for b in g["blank"]:
+        sc.frames[int(b)][:] = 0
+    ctx = gpu_ctx_752
+    ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
+    ctx.streams_reset(1)
+    for f in range(len(g["updated"])):
+        r = results_to_arrays(ctx.streams_step(sc.frames[f][None], [sc.times[f]]))[0]
+        assert bool(r["updated"]) == bool(g["updated"][f]), f
+        assert tuple(r["roi"]) == tuple(g["roi"][f]), f
+        assert r["n_det"] == g["n_det"][f], f
+        if r["updated"]:
+            k = int(g["n_corr"][f])
+            assert r["n_corr"] == k and np.array_equal(r["corr"][:2 * k].reshape(k, 2), g["corr"][f][:k]), f
+            assert r["gn_iters"] == g["iters"][f], f
+            dt, dr = pose_error(r["pose"].reshape(4, 4), g["pose"][f])
+            assert dt < 1e-6 and dr < 1e-6, (f, dt, dr)
