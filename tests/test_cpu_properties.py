@@ -129,3 +129,35 @@ def test_determine_roi_stays_inside_the_image_and_covers_the_predictions():
             assert (dist[:, 0] >= x - 2).all() and (dist[:, 0] <= x + w + 2).all() and (dist[:, 1] >= y - 2).all() and (dist[:, 1] <= y + h + 2).all()
             assert w >= np.ptp(dist[:, 0]) + b and h >= np.ptp(dist[:, 1]) + b
     assert n_inside >= 30
+
+
+def test_find_leds_on_a_roi_equals_find_leds_on_the_cropped_image():
+    """LEDDetector::findLeds works on image(ROI) only (led_detector.cpp:44-57: the blur sees a fresh Mat, BORDER_REFLECT_101 at the
+    ROI edge): searching an ROI must equal searching a physical copy of that crop and shifting the centres by ROI.tl in float32 —
+    the property the GPU tiles rely on when they never read pixels outside the ROI.  And integer shifts of the whole image shift
+    the distorted centres by exactly that amount."""
+    from tests.helpers import oracle_find_leds, random_blob_image
+    rng = np.random.default_rng(3)
+    K, D = synth.camera()
+    params = synth.Params()
+    n_cmp = 0
+    for it in range(80):
+        img = random_blob_image(rng, 240, 320, n_blobs=14, kind="mixed")
+        x, y = int(rng.integers(0, 200)), int(rng.integers(0, 150))
+        w, h = int(rng.integers(8, 320 - x + 1)), int(rng.integers(8, 240 - y + 1))
+        _, ce_roi = oracle_find_leds(img, (x, y, w, h), params, K, D)
+        crop = np.ascontiguousarray(img[y:y + h, x:x + w])
+        _, ce_crop = oracle_find_leds(crop, (0, 0, w, h), params, K, D)
+        assert len(ce_roi) == len(ce_crop)
+        if len(ce_crop):
+            shifted = ce_crop + np.array([x, y], np.float32)               # Point2f + Point2f
+            assert np.array_equal(ce_roi, shifted.astype(np.float32)), it
+            n_cmp += len(ce_crop)
+        # shift invariance (content moved by whole pixels inside a larger black frame)
+        big = np.zeros((300, 400), np.uint8)
+        dx, dy = int(rng.integers(0, 80)), int(rng.integers(0, 60))
+        big[dy:dy + 240, dx:dx + 320] = img
+        _, ce_a = oracle_find_leds(img, (0, 0, 320, 240), params, K, D)
+        _, ce_b = oracle_find_leds(big, (dx, dy, 320, 240), params, K, D)
+        assert np.array_equal(ce_b, (ce_a + np.array([dx, dy], np.float32)).astype(np.float32)) if len(ce_a) else len(ce_b) == 0
+    assert n_cmp > 20
