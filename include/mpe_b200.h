@@ -218,6 +218,13 @@ int mpe_set_k2_filter(mpe_ctx* ctx, int on);
 /* number of kernel launches issued by this context so far */
 long long mpe_kernel_launch_count(const mpe_ctx* ctx);
 
+/* ---- after the path ------------------------------------------------------------------------------------ */
+/* Host-only helper for callers without Eigen: the geometry_msgs/PoseWithCovariance fields MPENode::imageCallback fills from
+ * getPredictedPose() / getPoseCovariance() (monocular_pose_estimator.cpp:160-190): position = translation, orientation =
+ * Eigen::Quaterniond(R) as (x, y, z, w), covariance elems[j + 6*i] = cov(i, j).  Any output pointer may be NULL. */
+void mpe_pose_to_message(const double pose[16], const double cov[36], double position[3], double orientation_xyzw[4],
+                         double covariance[36]);
+
 #ifdef __cplusplus
 }
 #endif

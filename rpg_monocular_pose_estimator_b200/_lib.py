@@ -51,7 +51,7 @@ EXPORTS = [
     "mpe_estimate_batch_device", "mpe_estimate_batch_device_async", "mpe_fetch_results", "mpe_synchronize", "mpe_copy_poses_device",
     "mpe_streams_reset", "mpe_streams_set_frame_map", "mpe_streams_step_device", "mpe_streams_step", "mpe_set_graph_replay", "mpe_set_ingest_mode", "mpe_get_ingest_stats", "mpe_set_k2_filter",
     "mpe_enable_kernel_timing", "mpe_get_kernel_times",
-    "mpe_kernel_launch_count",
+    "mpe_kernel_launch_count", "mpe_pose_to_message",
 ]
 
 _LIB = None
@@ -99,6 +99,7 @@ def load_library():
         "mpe_enable_kernel_timing": ([vp, C.c_int], C.c_int),
         "mpe_get_kernel_times": ([vp, fp], C.c_int),
         "mpe_kernel_launch_count": ([vp], C.c_longlong),
+        "mpe_pose_to_message": ([dp, dp, dp, dp, dp], None),
     }
     for name in EXPORTS:
         fn = getattr(L, name)      # AttributeError if the symbol is missing

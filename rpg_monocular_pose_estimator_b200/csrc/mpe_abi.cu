@@ -1084,4 +1084,39 @@ int mpe_get_kernel_times(mpe_ctx* c, float ms_out[5]) {
 
 long long mpe_kernel_launch_count(const mpe_ctx* c) { return c ? c->launches : 0; }
 
+// Host-only: the fields MPENode::imageCallback fills after estimateBodyPose (monocular_pose_estimator.cpp:160-190).  The quaternion
+// follows the published algorithm of Eigen's Quaterniond(Matrix3d) constructor (trace branch, else the largest diagonal entry).
+void mpe_pose_to_message(const double pose[16], const double cov[36], double position[3], double orientation_xyzw[4], double covariance[36]) {
+  if (!pose) return;
+  if (position) { position[0] = pose[3]; position[1] = pose[7]; position[2] = pose[11]; }
+  if (orientation_xyzw) {
+    auto m = [&](int r, int c) { return pose[4 * r + c]; };
+    double q[4];                                             // x, y, z, w
+    double t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > 0.0) {
+      t = std::sqrt(t + 1.0);
+      q[3] = 0.5 * t;
+      t = 0.5 / t;
+      q[0] = (m(2, 1) - m(1, 2)) * t;
+      q[1] = (m(0, 2) - m(2, 0)) * t;
+      q[2] = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+      q[i] = 0.5 * t;
+      t = 0.5 / t;
+      q[3] = (m(k, j) - m(j, k)) * t;
+      q[j] = (m(j, i) + m(i, j)) * t;
+      q[k] = (m(k, i) + m(i, k)) * t;
+    }
+    for (int e = 0; e < 4; ++e) orientation_xyzw[e] = q[e];
+  }
+  if (covariance && cov)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) covariance[j + 6 * i] = cov[6 * i + j];     // elems[j + 6*i] = cov(i, j)
+}
+
 }  // extern "C"

@@ -235,3 +235,27 @@ def test_host_mirror_small_math_matches_oracle():
         est = pose_oracle.PoseEstimatorOracle(K, D, synth.markers(5), synth.Params())
         est.L.mpeo_set_predicted_pixels(est.h, dp(px), 5)
         assert mpe.LEDDetector.determineROI(px, (752, 480), 20, K, D) == est.determine_roi(752, 480)
+
+
+def test_pose_to_message_matches_scipy_and_node_packing():
+    """mpe_pose_to_message (host-only): what MPENode::imageCallback packs (monocular_pose_estimator.cpp:160-190)."""
+    from scipy.spatial.transform import Rotation
+    L = _lib.load_library()
+    rng = np.random.default_rng(4)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for i in range(300):
+        rv = rng.normal(size=3)
+        rv *= rng.uniform(0, math.pi) / np.linalg.norm(rv)
+        if i % 10 == 0:
+            rv *= (math.pi - 1e-9) / np.linalg.norm(rv)              # trace near -1: the largest-diagonal branch
+        Rm = Rotation.from_rotvec(rv).as_matrix()
+        T = np.eye(4); T[:3, :3] = Rm; T[:3, 3] = rng.normal(size=3)
+        cov = rng.normal(size=(6, 6))
+        pos, q, cm = np.zeros(3), np.zeros(4), np.zeros(36)
+        L.mpe_pose_to_message(dp(np.ascontiguousarray(T)), dp(np.ascontiguousarray(cov)), dp(pos), dp(q), dp(cm))
+        assert np.array_equal(pos, T[:3, 3])
+        assert abs(np.linalg.norm(q) - 1) < 1e-12
+        assert np.abs(Rotation.from_quat(q).as_matrix() - Rm).max() < 1e-12
+        if np.trace(Rm) > 0:
+            assert q[3] > 0                                           # Eigen's trace branch: w = sqrt(trace + 1) / 2
+        assert np.array_equal(cm.reshape(6, 6), cov)                  # elems[j + 6*i] = cov(i, j)
