@@ -291,33 +291,47 @@ unsigned num_combinations(unsigned N, unsigned K) { return factorial_u((int)N) /
 
 // ---------------------------------------------------------------- 6x6 and 3x3 dense helpers
 
-// Solve A x = b for symmetric A with an LDL^T factorisation with diagonal pivoting (largest
-// |diagonal| first), the scheme Eigen's LDLT uses (L/src/pose_estimator.cpp:778).
+// Solve A x = b for symmetric A: LDL^T with diagonal pivoting as Eigen's LDLT documents it (L/src/pose_estimator.cpp:778),
+// operation for operation what oracle/eigen_shim's LDLT does, so that the Gauss-Newton iteration count (exit test at the
+// rounding floor, :786) equals the count of the reference sources built against that stand-in:
+//   * lower triangle only, left-looking: column k is formed from the original entries and the finished columns 0..k-1;
+//   * the pivot of step k is the largest |diagonal| among the NOT YET UPDATED entries k..5 (first one on ties);
+//   * solve: P, unit-lower forward substitution, D (a pivot below DBL_MIN gives 0), backward substitution, P^T.
 void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) {
-  double A[6][6];
-  int perm[6];
-  for (int i = 0; i < 6; ++i) { perm[i] = i; for (int j = 0; j < 6; ++j) A[i][j] = Ain[i * 6 + j]; }
-  // In-place: lower triangle holds L, diagonal holds D.
+  double m[6][6];
+  int tr[6];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) m[i][j] = Ain[i * 6 + j];
   for (int k = 0; k < 6; ++k) {
-    int p = k; double best = std::fabs(A[k][k]);
-    for (int i = k + 1; i < 6; ++i) if (std::fabs(A[i][i]) > best) { best = std::fabs(A[i][i]); p = i; }
-    if (p != k) {
-      for (int j = 0; j < 6; ++j) std::swap(A[k][j], A[p][j]);
-      for (int i = 0; i < 6; ++i) std::swap(A[i][k], A[i][p]);
-      std::swap(perm[k], perm[p]);
+    int big = k; double best = std::fabs(m[k][k]);
+    for (int i = k + 1; i < 6; ++i) if (std::fabs(m[i][i]) > best) { best = std::fabs(m[i][i]); big = i; }
+    tr[k] = big;
+    if (big != k) {
+      for (int j = 0; j < k; ++j) std::swap(m[k][j], m[big][j]);
+      for (int i = big + 1; i < 6; ++i) std::swap(m[i][k], m[i][big]);
+      std::swap(m[k][k], m[big][big]);
+      for (int i = k + 1; i < big; ++i) std::swap(m[i][k], m[big][i]);
     }
-    double d = A[k][k];
-    for (int i = k + 1; i < 6; ++i)
-      for (int j = k + 1; j <= i; ++j) A[i][j] -= A[i][k] * A[j][k] / d;  // Schur update, column still unscaled
-    for (int i = k + 1; i < 6; ++i) A[i][k] /= d;                        // now L(i,k)
-    for (int i = k + 1; i < 6; ++i) for (int j = k + 1; j < i; ++j) A[j][i] = A[i][j];
+    if (k > 0) {
+      double temp[6];
+      for (int j = 0; j < k; ++j) temp[j] = m[j][j] * m[k][j];
+      double s = m[k][0] * temp[0];
+      for (int j = 1; j < k; ++j) s += m[k][j] * temp[j];
+      m[k][k] -= s;
+      for (int i = k + 1; i < 6; ++i) {
+        double t = m[i][0] * temp[0];
+        for (int j = 1; j < k; ++j) t += m[i][j] * temp[j];
+        m[i][k] -= t;
+      }
+    }
+    const double akk = m[k][k];
+    if (std::fabs(akk) > 0.0) for (int i = k + 1; i < 6; ++i) m[i][k] /= akk;
   }
-  double y[6];
-  for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
-  for (int i = 0; i < 6; ++i) y[i] /= A[i][i];
-  for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+  for (int i = 0; i < 6; ++i) x[i] = bin[i];
+  for (int k = 0; k < 6; ++k) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
+  for (int j = 0; j < 6; ++j) for (int i = j + 1; i < 6; ++i) x[i] -= m[i][j] * x[j];
+  for (int i = 0; i < 6; ++i) { if (std::fabs(m[i][i]) > std::numeric_limits<double>::min()) x[i] /= m[i][i]; else x[i] = 0.0; }
+  for (int j = 5; j >= 0; --j) for (int i = 0; i < j; ++i) x[i] -= m[j][i] * x[j];
+  for (int k = 5; k >= 0; --k) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
 }
 
 // General 6x6 inverse, LU with partial pivoting (Eigen's inverse() for size > 4 goes through
@@ -677,7 +691,7 @@ struct Oracle {
     double phi = 0;
     // R.isApprox(I, 1e-10): ||R-I||_F^2 <= 1e-20 * min(||R||_F^2, ||I||_F^2)
     double dn = 0, rn = 0;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double I = (i == j) ? 1.0 : 0.0; dn += (R.m[i][j] - I) * (R.m[i][j] - I); rn += R.m[i][j] * R.m[i][j]; }
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { double I = (i == j) ? 1.0 : 0.0; dn += (R.m[i][j] - I) * (R.m[i][j] - I); rn += R.m[i][j] * R.m[i][j]; }  // column-major, as Eigen stores R
     bool approx_identity = dn <= 1e-10 * 1e-10 * std::min(rn, 3.0);
     if (!approx_identity) {
       double temp = (R.m[0][0] + R.m[1][1] + R.m[2][2] - 1) / 2;
@@ -699,8 +713,10 @@ struct Oracle {
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A_inv.m[i][j] = (i == j) ? 1.0 : 0.0;
     } else {
       double k = (2 * std::sin(w_norm) - w_norm * (1 + std::cos(w_norm))) / (2 * w_norm * w_norm * std::sin(w_norm));
-      M3 w2 = mul(w_hat, w_hat);
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A_inv.m[i][j] = ((i == j) ? 1.0 : 0.0) - w_hat.m[i][j] / 2 + k * w2.m[i][j];
+      // `I - w_hat / 2 + k * w_hat * w_hat` parses as (I - w_hat/2) + ((k * w_hat) * w_hat)   (:1056-1057)
+      M3 kw; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) kw.m[i][j] = k * w_hat.m[i][j];
+      M3 w2 = mul(kw, w_hat);
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A_inv.m[i][j] = (((i == j) ? 1.0 : 0.0) - w_hat.m[i][j] / 2) + w2.m[i][j];
     }
     V3 ups = mul(A_inv, t);
     xi[0] = ups[0]; xi[1] = ups[1]; xi[2] = ups[2]; xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];

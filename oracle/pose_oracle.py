@@ -22,54 +22,58 @@ def build(force: bool = False) -> str:
     return so
 
 
+dp, up, ip = C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_int)
+# (name, argtypes, restype) of the C API; oracle/ref_pose.py binds the mper_* twins of the reference build with the same table
+SIGNATURES = [
+    ("mpeo_destroy", [C.c_void_p], None),
+    ("mpeo_solve_quartic", [dp, dp], C.c_int),
+    ("mpeo_p3p", [dp, dp, dp], C.c_int),
+    ("mpeo_set_camera", [C.c_void_p, dp, dp, C.c_int], None),
+    ("mpeo_set_markers", [C.c_void_p, dp, C.c_int], None),
+    ("mpeo_set_params", [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double], None),
+    ("mpeo_set_histogram_threshold", [C.c_void_p, C.c_uint], None),
+    ("mpeo_get_histogram_threshold", [C.c_void_p], C.c_uint),
+    ("mpeo_set_image_points", [C.c_void_p, dp, C.c_int], None),
+    ("mpeo_get_image_vectors", [C.c_void_p, dp], C.c_int),
+    ("mpeo_initialise", [C.c_void_p], C.c_uint),
+    ("mpeo_get_histogram", [C.c_void_p, up], C.c_int),
+    ("mpeo_get_counters", [C.c_void_p, C.POINTER(C.c_ulonglong)], None),
+    ("mpeo_get_correspondences", [C.c_void_p, up], C.c_int),
+    ("mpeo_set_correspondences", [C.c_void_p, up, C.c_int], None),
+    ("mpeo_check_correspondences", [C.c_void_p], C.c_uint),
+    ("mpeo_find_correspondences", [C.c_void_p], None),
+    ("mpeo_optimise_pose", [C.c_void_p], C.c_int),
+    ("mpeo_optimise_and_update_pose", [C.c_void_p], None),
+    ("mpeo_last_gn_iterations", [C.c_void_p], C.c_int),
+    ("mpeo_update_pose", [C.c_void_p], None),
+    ("mpeo_get_predicted_pose", [C.c_void_p, dp], None),
+    ("mpeo_set_predicted_pose", [C.c_void_p, dp, C.c_double], None),
+    ("mpeo_get_current_pose", [C.c_void_p, dp], None),
+    ("mpeo_get_previous_pose", [C.c_void_p, dp], None),
+    ("mpeo_set_state", [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_uint], None),
+    ("mpeo_get_covariance", [C.c_void_p, dp], None),
+    ("mpeo_set_predicted_time", [C.c_void_p, C.c_double], None),
+    ("mpeo_get_predicted_time", [C.c_void_p], C.c_double),
+    ("mpeo_it_since_initialized", [C.c_void_p], C.c_uint),
+    ("mpeo_predict_pose", [C.c_void_p, C.c_double], None),
+    ("mpeo_predict_marker_positions", [C.c_void_p], None),
+    ("mpeo_get_predicted_pixels", [C.c_void_p, dp], C.c_int),
+    ("mpeo_set_predicted_pixels", [C.c_void_p, dp, C.c_int], None),
+    ("mpeo_determine_roi", [C.c_void_p, C.c_int, C.c_int, C.c_int, ip], None),
+    ("mpeo_project2d", [C.c_void_p, dp, dp, dp], None),
+    ("mpeo_exponential_map", [dp, dp], None),
+    ("mpeo_logarithm_map", [dp, dp], None),
+    ("mpeo_distort_point", [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_float)], None),
+    ("mpeo_cold_pose_batch", [C.c_void_p, dp, ip, C.c_int, C.c_int, dp, ip], C.c_int),
+        ]
+
+
 def lib():
     global _LIB
     if _LIB is None:
         L = C.CDLL(build())
-        dp, up, ip = C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_int)
         L.mpeo_create.restype = C.c_void_p
-        for name, args, res in [
-            ("mpeo_destroy", [C.c_void_p], None),
-            ("mpeo_solve_quartic", [dp, dp], C.c_int),
-            ("mpeo_p3p", [dp, dp, dp], C.c_int),
-            ("mpeo_set_camera", [C.c_void_p, dp, dp, C.c_int], None),
-            ("mpeo_set_markers", [C.c_void_p, dp, C.c_int], None),
-            ("mpeo_set_params", [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double], None),
-            ("mpeo_set_histogram_threshold", [C.c_void_p, C.c_uint], None),
-            ("mpeo_get_histogram_threshold", [C.c_void_p], C.c_uint),
-            ("mpeo_set_image_points", [C.c_void_p, dp, C.c_int], None),
-            ("mpeo_get_image_vectors", [C.c_void_p, dp], C.c_int),
-            ("mpeo_initialise", [C.c_void_p], C.c_uint),
-            ("mpeo_get_histogram", [C.c_void_p, up], C.c_int),
-            ("mpeo_get_counters", [C.c_void_p, C.POINTER(C.c_ulonglong)], None),
-            ("mpeo_get_correspondences", [C.c_void_p, up], C.c_int),
-            ("mpeo_set_correspondences", [C.c_void_p, up, C.c_int], None),
-            ("mpeo_check_correspondences", [C.c_void_p], C.c_uint),
-            ("mpeo_find_correspondences", [C.c_void_p], None),
-            ("mpeo_optimise_pose", [C.c_void_p], C.c_int),
-            ("mpeo_optimise_and_update_pose", [C.c_void_p], None),
-            ("mpeo_last_gn_iterations", [C.c_void_p], C.c_int),
-            ("mpeo_update_pose", [C.c_void_p], None),
-            ("mpeo_get_predicted_pose", [C.c_void_p, dp], None),
-            ("mpeo_set_predicted_pose", [C.c_void_p, dp, C.c_double], None),
-            ("mpeo_get_current_pose", [C.c_void_p, dp], None),
-            ("mpeo_get_previous_pose", [C.c_void_p, dp], None),
-            ("mpeo_set_state", [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_uint], None),
-            ("mpeo_get_covariance", [C.c_void_p, dp], None),
-            ("mpeo_set_predicted_time", [C.c_void_p, C.c_double], None),
-            ("mpeo_get_predicted_time", [C.c_void_p], C.c_double),
-            ("mpeo_it_since_initialized", [C.c_void_p], C.c_uint),
-            ("mpeo_predict_pose", [C.c_void_p, C.c_double], None),
-            ("mpeo_predict_marker_positions", [C.c_void_p], None),
-            ("mpeo_get_predicted_pixels", [C.c_void_p, dp], C.c_int),
-            ("mpeo_set_predicted_pixels", [C.c_void_p, dp, C.c_int], None),
-            ("mpeo_determine_roi", [C.c_void_p, C.c_int, C.c_int, C.c_int, ip], None),
-            ("mpeo_project2d", [C.c_void_p, dp, dp, dp], None),
-            ("mpeo_exponential_map", [dp, dp], None),
-            ("mpeo_logarithm_map", [dp, dp], None),
-            ("mpeo_distort_point", [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_float)], None),
-            ("mpeo_cold_pose_batch", [C.c_void_p, dp, ip, C.c_int, C.c_int, dp, ip], C.c_int),
-        ]:
+        for name, args, res in SIGNATURES:
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = res
@@ -101,8 +105,8 @@ class PoseEstimatorOracle:
     """Mirror of monocular_pose_estimator::PoseEstimator (pose_estimator.h:52-803) on the CPU oracle."""
     MIN_NUM_LEDS_DETECTED = 4   # pose_estimator.h:78
 
-    def __init__(self, K, D, markers, params):
-        self.L = lib()
+    def __init__(self, K, D, markers, params, _lib=None):
+        self.L = _lib if _lib is not None else lib()
         self.h = C.c_void_p(self.L.mpeo_create())
         self.K = np.ascontiguousarray(K, np.float64)
         self.D = np.ascontiguousarray(D, np.float64)
