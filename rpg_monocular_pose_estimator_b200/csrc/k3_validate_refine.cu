@@ -117,69 +117,84 @@ __device__ void svd3(const double Ain[3][3], double U[3][3], double V[3][3]) {
   }
 }
 
-// Symmetric solve by LDL^T with diagonal pivoting; same arithmetic, in the same order, as oracle ldlt_solve6.
+// Symmetric solve by LDL^T with diagonal pivoting; same arithmetic, in the same order, as oracle ldlt_solve6 (which is the
+// scheme Eigen's LDLT documents and oracle/eigen_shim implements: lower triangle only, left-looking, the pivot of step k
+// is the largest |diagonal| among the not yet updated entries k..5; solve = P, L, D with a zero-pivot guard, L^T, P^T).
 // Written with compile-time indices only (the pivot exchange is a predicated swap over the unrolled candidates), so
 // the 6x6 system stays in registers.  NB: the first version indexed local arrays with the run-time pivot; nvcc 12.9
 // (-O3, sm_100a) miscompiled it inside this kernel (wrong solution, fixed by -Xcicc -O1) — see DESIGN.md, "toolchain".
 __device__ __forceinline__ void swap_d(double& a, double& b) { double t = a; a = b; b = t; }
 
 __device__ __forceinline__ void ldlt_solve6(const double Ain[36], const double bin[6], double x[6]) {
-  double A[6][6], y[6];
-  int piv[6];
+  double m[6][6], y[6];   // only m[i][j], i >= j, is used
+  int tr[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     y[i] = bin[i];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) A[i][j] = Ain[i * 6 + j];
+    for (int j = 0; j <= i; ++j) m[i][j] = Ain[i * 6 + j];
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    int p = k;
-    double best = fabs(A[k][k]);
+    int big = k;
+    double best = fabs(m[k][k]);
 #pragma unroll
     for (int i = k + 1; i < 6; ++i) {
-      double v = fabs(A[i][i]);
-      if (v > best) { best = v; p = i; }
+      const double v = fabs(m[i][i]);
+      if (v > best) { best = v; big = i; }
     }
-    piv[k] = p;
+    tr[k] = big;
 #pragma unroll
     for (int q = k + 1; q < 6; ++q) {
-      if (p == q) {   // symmetric exchange of rows/columns k and q, right-hand side follows
+      if (big == q) {   // symmetric exchange of rows/columns k and q inside the lower triangle; the right-hand side follows
 #pragma unroll
-        for (int j = 0; j < 6; ++j) swap_d(A[k][j], A[q][j]);
+        for (int j = 0; j < k; ++j) swap_d(m[k][j], m[q][j]);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) swap_d(A[i][k], A[i][q]);
+        for (int i = q + 1; i < 6; ++i) swap_d(m[i][k], m[i][q]);
+        swap_d(m[k][k], m[q][q]);
+#pragma unroll
+        for (int i = k + 1; i < q; ++i) swap_d(m[i][k], m[q][i]);
         swap_d(y[k], y[q]);
       }
     }
-    double d = A[k][k];
+    if (k > 0) {
+      double temp[6];
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i)
+      for (int j = 0; j < k; ++j) temp[j] = m[j][j] * m[k][j];
+      double s = m[k][0] * temp[0];
 #pragma unroll
-      for (int j = k + 1; j <= i; ++j) A[i][j] -= A[i][k] * A[j][k] / d;
+      for (int j = 1; j < k; ++j) s += m[k][j] * temp[j];
+      m[k][k] -= s;
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
+      for (int i = k + 1; i < 6; ++i) {
+        double t = m[i][0] * temp[0];
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i)
+        for (int j = 1; j < k; ++j) t += m[i][j] * temp[j];
+        m[i][k] -= t;
+      }
+    }
+    const double akk = m[k][k];
+    if (fabs(akk) > 0.0) {
 #pragma unroll
-      for (int j = k + 1; j < i; ++j) A[j][i] = A[i][j];
+      for (int i = k + 1; i < 6; ++i) m[i][k] /= akk;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+    for (int j = 0; j < i; ++j) y[i] -= m[i][j] * y[j];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) y[i] /= A[i][i];
+  for (int i = 0; i < 6; ++i) { if (fabs(m[i][i]) > 2.2250738585072014e-308) y[i] /= m[i][i]; else y[i] = 0.0; }
 #pragma unroll
   for (int i = 5; i >= 0; --i)
 #pragma unroll
-    for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+    for (int j = 5; j > i; --j) y[i] -= m[j][i] * y[j];
   // undo the exchanges (x = P^T y): transpositions in reverse order
 #pragma unroll
   for (int k = 5; k >= 0; --k) {
 #pragma unroll
     for (int q = k + 1; q < 6; ++q)
-      if (piv[k] == q) swap_d(y[k], y[q]);
+      if (tr[k] == q) swap_d(y[k], y[q]);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) x[i] = y[i];
@@ -832,7 +847,6 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
             acc += Jj[r] * Jj[c] + Jj[6 + r] * Jj[6 + c];
           }
           S.A0[r * 6 + c] = acc; S.A0[c * 6 + r] = acc;            // J0[r]*J0[c] == J0[c]*J0[r]: the reference's two entries are equal
-          S.Aw[r * 6 + c] = acc; S.Aw[c * 6 + r] = acc;
         } else {
           const int r = e - 21;
           for (int j = 0; j < k; ++j) {
@@ -845,35 +859,47 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
       }
     }
     __syncwarp();
-    // ---- 3. dT = A.ldlt().solve(b)  (:778), arithmetic of ldlt_solve6
+    // ---- 3. dT = A.ldlt().solve(b)  (:778), arithmetic of ldlt_solve6: left-looking LDL^T of P A P^T.  Entries that have not
+    //         been reached yet are the original ones, so the exchanges are a permutation of labels (nibbles of pk) and no
+    //         data moves: L(i,j) = Aw[perm[i]][j], untouched entries = A0[perm[i]][perm[j]].
     uint32_t pk = 0x543210u;                                       // perm[i] = nibble i
+    double Dg[6] = {1, 1, 1, 1, 1, 1};
 #pragma unroll
     for (int kk = 0; kk < 6; ++kk) {
-      int pkk = 0;
-      double d = 1.0;
       if (run) {
         int p = kk;
-        double best = fabs(S.Aw[nib(pk, kk) * 7]);
+        double best = fabs(S.A0[nib(pk, kk) * 7]);
 #pragma unroll
         for (int i = kk + 1; i < 6; ++i) {
-          const double v = fabs(S.Aw[nib(pk, i) * 7]);
+          const double v = fabs(S.A0[nib(pk, i) * 7]);
           if (v > best) { best = v; p = i; }
         }
         pk = nib_swap(pk, kk, p);
-        pkk = nib(pk, kk);
-        d = S.Aw[pkk * 7];
-        const int n_tr = 5 - kk, n_pairs = n_tr * (n_tr + 1) / 2;
-        for (int e = gl; e < n_pairs; e += G) {                     // Schur update of the trailing lower triangle (column kk still unscaled)
-          int io = 0, jo = e;
-          while (jo > io) { jo -= io + 1; ++io; }
-          const int pi = nib(pk, kk + 1 + io), pj = nib(pk, kk + 1 + jo);
-          const double v = S.Aw[pi * 6 + pj] - S.Aw[pi * 6 + pkk] * S.Aw[pj * 6 + pkk] / d;
-          S.Aw[pi * 6 + pj] = v; S.Aw[pj * 6 + pi] = v;
+        const int pkk = nib(pk, kk);
+        double temp[6] = {0, 0, 0, 0, 0, 0};
+        double dk = S.A0[pkk * 7];
+        if (kk > 0) {
+#pragma unroll
+          for (int j = 0; j < kk; ++j) temp[j] = Dg[j] * S.Aw[pkk * 6 + j];
+          double sacc = S.Aw[pkk * 6] * temp[0];
+#pragma unroll
+          for (int j = 1; j < kk; ++j) sacc += S.Aw[pkk * 6 + j] * temp[j];
+          dk -= sacc;
+        }
+        Dg[kk] = dk;
+        for (int i = kk + 1 + gl; i < 6; i += G) {                  // column kk of L, one row per lane
+          const int pi = nib(pk, i);
+          double v = S.A0[pi * 6 + pkk];
+          if (kk > 0) {
+            double t = S.Aw[pi * 6] * temp[0];
+#pragma unroll
+            for (int j = 1; j < kk; ++j) t += S.Aw[pi * 6 + j] * temp[j];
+            v -= t;
+          }
+          if (fabs(dk) > 0.0) v /= dk;
+          S.Aw[pi * 6 + kk] = v;
         }
       }
-      __syncwarp();
-      if (run)
-        for (int i = kk + 1 + gl; i < 6; i += G) { const int pi = nib(pk, i); S.Aw[pi * 6 + pkk] = S.Aw[pi * 6 + pkk] / d; }   // L(i,kk)
       __syncwarp();
     }
     double dT[6] = {0, 0, 0, 0, 0, 0};
@@ -884,13 +910,13 @@ __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < i; ++j) y[i] -= S.Aw[nib(pk, i) * 6 + nib(pk, j)] * y[j];
+        for (int j = 0; j < i; ++j) y[i] -= S.Aw[nib(pk, i) * 6 + j] * y[j];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) y[i] /= S.Aw[nib(pk, i) * 7];
+      for (int i = 0; i < 6; ++i) { if (fabs(Dg[i]) > 2.2250738585072014e-308) y[i] /= Dg[i]; else y[i] = 0.0; }
 #pragma unroll
       for (int i = 5; i >= 0; --i)
 #pragma unroll
-        for (int j = i + 1; j < 6; ++j) y[i] -= S.Aw[nib(pk, j) * 6 + nib(pk, i)] * y[j];
+        for (int j = 5; j > i; --j) y[i] -= S.Aw[nib(pk, j) * 6 + i] * y[j];
       if (gl == 0) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) S.dT[nib(pk, i)] = y[i];

@@ -94,8 +94,8 @@ __device__ void logarithm_map(const M4& trans, double xi[6]) {
   for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r][c] = trans.m[4 * r + c]; t[r] = trans.m[4 * r + 3]; }
   double w_hat[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double dn = 0, rn = 0;
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) { const double I = (i == j) ? 1.0 : 0.0; dn += (R[i][j] - I) * (R[i][j] - I); rn += R[i][j] * R[i][j]; }
+  for (int j = 0; j < 3; ++j)      // column-major, the order Eigen's squaredNorm() visits a Matrix3d
+    for (int i = 0; i < 3; ++i) { const double I = (i == j) ? 1.0 : 0.0; dn += (R[i][j] - I) * (R[i][j] - I); rn += R[i][j] * R[i][j]; }
   const bool approx_identity = dn <= 1e-10 * 1e-10 * fmin(rn, 3.0);     // R.isApprox(I, 1e-10)
   if (!approx_identity) {
     double temp = (R[0][0] + R[1][1] + R[2][2] - 1) / 2;
@@ -118,8 +118,9 @@ __device__ void logarithm_map(const M4& trans, double xi[6]) {
     const double k = (2 * sin(w_norm) - w_norm * (1 + cos(w_norm))) / (2 * w_norm * w_norm * sin(w_norm));
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) {
-        const double w2 = w_hat[i][0] * w_hat[0][j] + w_hat[i][1] * w_hat[1][j] + w_hat[i][2] * w_hat[2][j];
-        A_inv[i][j] = ((i == j) ? 1.0 : 0.0) - w_hat[i][j] / 2 + k * w2;
+        // `I - w_hat / 2 + k * w_hat * w_hat` parses as (I - w_hat/2) + ((k * w_hat) * w_hat)   (:1056-1057)
+        const double w2 = (k * w_hat[i][0]) * w_hat[0][j] + (k * w_hat[i][1]) * w_hat[1][j] + (k * w_hat[i][2]) * w_hat[2][j];
+        A_inv[i][j] = (((i == j) ? 1.0 : 0.0) - w_hat[i][j] / 2) + w2;
       }
   }
   for (int r = 0; r < 3; ++r) xi[r] = A_inv[r][0] * t[0] + A_inv[r][1] * t[1] + A_inv[r][2] * t[2];
