@@ -16,6 +16,7 @@
 // FP64 / latency bound, not HBM bound: it reads < 1 KB per frame.  Compiled with -fmad=false.
 #include "mpe_internal.cuh"
 #include "p3p_device.cuh"
+#include "p3p_tier1.cuh"
 #include <cstdlib>
 
 namespace mpe {
@@ -98,21 +99,31 @@ constexpr double kCondMin = 1e-6;        // sine of the angle that defines a fra
 __global__ void marker_triples_kernel(const DevPoseParams pp, int n_perm, double* __restrict__ tab) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_perm) return;
-  int o0, o1, o2;
-  unrank_perm3(pp.n_obj, j, o0, o1, o2);
+  int o0, o1, o2, oa, ob, oc;
+  unrank_perm3(pp.n_obj, j, o0, o1, o2, oa, ob, oc);
   const double* mk = pp.markers;
   P3PWorld W;
   p3p_world_frame(v_make(mk[3 * o0], mk[3 * o0 + 1], mk[3 * o0 + 2]), v_make(mk[3 * o1], mk[3 * o1 + 1], mk[3 * o1 + 2]),
                   v_make(mk[3 * o2], mk[3 * o2 + 1], mk[3 * o2 + 2]), W);
-  const double f[kTripleFields] = {W.n1.x, W.n1.y, W.n1.z, W.n2.x, W.n2.y, W.n2.z, W.n3.x, W.n3.y, W.n3.z, W.P1.x, W.P1.y, W.P1.z,
-                                   W.p_1, W.p_2, W.d_12, 0.0};
-  for (int k = 0; k < kTripleFields - 1; ++k) tab[(size_t)k * n_perm + j] = f[k];
+  const double f[15] = {W.n1.x, W.n1.y, W.n1.z, W.n2.x, W.n2.y, W.n2.z, W.n3.x, W.n3.y, W.n3.z, W.P1.x, W.P1.y, W.P1.z,
+                        W.p_1, W.p_2, W.d_12};
+  for (int k = 0; k < 15; ++k) tab[(size_t)k * n_perm + j] = f[k];
   double code = 0.0;
   if (!(W.cross_norm == 0.0)) {
     const double len13 = sqrt(W.p_1 * W.p_1 + W.p_2 * W.p_2);        // |P3 - P1| (P3 has no z component in the world frame)
     code = (W.cross_norm > kCondMin * W.d_12 * len13) ? 2.0 : 1.0;
   }
-  tab[(size_t)(kTripleFields - 1) * n_perm + j] = code;
+  tab[(size_t)15 * n_perm + j] = code;
+  tab[(size_t)16 * n_perm + j] = (double)(o0 | (o1 << 4) | (o2 << 8) | (oa << 12) | (ob << 16) | (oc << 20));
+  // tier 1: the unused LEDs in this triple's world frame, X_N = N (X - P1), in LED order
+  const int nu = pp.n_obj - 3;
+  for (int m = 0; m < nu; ++m) {
+    const int ll = nth_unused(m, oa, ob, oc);
+    const v3 dx = v_sub(v_make(mk[3 * ll], mk[3 * ll + 1], mk[3 * ll + 2]), W.P1);
+    tab[(size_t)(kTripleXN + 3 * m) * n_perm + j] = v_dot(W.n1, dx);
+    tab[(size_t)(kTripleXN + 3 * m + 1) * n_perm + j] = v_dot(W.n2, dx);
+    tab[(size_t)(kTripleXN + 3 * m + 2) * n_perm + j] = v_dot(W.n3, dx);
+  }
 }
 
 cudaError_t launch_marker_triples(const DevPoseParams& pp, double* table, cudaStream_t st) {
@@ -145,6 +156,12 @@ __global__ void combo_setup_kernel(const K2Args a) {
     o[0] = Cm.e1.x; o[1] = Cm.e1.y; o[2] = Cm.e1.z; o[3] = Cm.e2.x; o[4] = Cm.e2.y; o[5] = Cm.e2.z;
     o[6] = Cm.e3.x; o[7] = Cm.e3.y; o[8] = Cm.e3.z; o[9] = Cm.f_1; o[10] = Cm.f_2; o[11] = Cm.b;
     o[12] = (double)(Cm.swap | ((Cm.sin12 > kCondMin) ? 2 : 0));
+    o[13] = (double)(d0 | (d1 << 4) | (d2 << 8));
+    // tier 1: Mc = K [e1 e2 e3] (columns), row-major
+    const double* K = a.cam.K;
+    const v3 e[3] = {Cm.e1, Cm.e2, Cm.e3};
+    for (int r = 0; r < 3; ++r)
+      for (int q = 0; q < 3; ++q) o[14 + 3 * r + q] = K[3 * r] * e[q].x + K[3 * r + 1] * e[q].y + K[3 * r + 2] * e[q].z;
   }
 }
 
@@ -406,6 +423,213 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
   }
 }
 
+// ---- the two-tier sweep --------------------------------------------------------------------------------------------------
+// Tier 1 (p3p_tier1.cuh) answers "certainly no vote" for ~95 % of the problems at about a quarter of the instructions of the
+// exact solve; the rest is parked in a shared-memory queue of (frame, problem) pairs, and whenever a full block of them has
+// accumulated — across frames: the CTA is persistent — every thread takes one and runs the reference's arithmetic
+// (p3p_quartic, four back-substitutions, exact scoring).  A CTA flattens `group` consecutive frames into one problem sequence
+// so that its passes are full (600 problems of one 5-LED frame fill 2.3 passes of 256 threads, 1200 of two fill 4.7).
+template <bool kBBox>
+__device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const double* __restrict__ tt, int n_perm, int tj,
+                                            uint32_t ids, int n_det, int n_obj, const double* __restrict__ det, double r, const double bb[4]) {
+  T1Roots R;
+  const double f_1 = cb[9], f_2 = cb[10], b = cb[11];
+  const double p_1 = tt[(size_t)12 * n_perm + tj], p_2 = tt[(size_t)13 * n_perm + tj], d_12 = tt[(size_t)14 * n_perm + tj];
+  t1_quartic_roots(f_1, f_2, b, p_1, p_2, d_12, R);
+  if (R.maybe) return true;
+  const int d0 = ids & 15, d1 = (ids >> 4) & 15, d2 = (ids >> 8) & 15;
+  const int nu_obj = n_obj - 3, nu_det = n_det - 3;
+  const double r2 = r * r;
+  double Mc[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) Mc[e] = cb[14 + e];
+  bool maybe = false;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    T1Pose P;
+    const int st = t1_pose(R.rho[k], f_1, f_2, b, p_1, p_2, d_12, P);
+    if (st == 0) continue;
+    if (st == 2) { maybe = true; break; }
+    for (int m = 0; m < nu_obj; ++m) {
+      const double X0 = tt[(size_t)(kTripleXN + 3 * m) * n_perm + tj], X1 = tt[(size_t)(kTripleXN + 3 * m + 1) * n_perm + tj],
+                   X2 = tt[(size_t)(kTripleXN + 3 * m + 2) * n_perm + tj];
+      double au, av, az, l1;
+      t1_project(P, Mc, X0, X1, X2, au, av, az, l1);
+      // close to the camera plane (or to the camera itself): the division-free comparison is not trusted
+      const bool near_plane = !(fabs(az) >= 1e-3 * l1) || !(l1 >= 1e-3 * d_12);
+      maybe = maybe || near_plane;
+      if (kBBox) {
+        const double aaz = fabs(az);
+        const bool outside = fabs(au - bb[0] * az) > (bb[2] + r) * aaz || fabs(av - bb[1] * az) > (bb[3] + r) * aaz;
+        if (outside && !near_plane) continue;
+      }
+      const double lim = r2 * (az * az);
+      for (int i = 0; i < nu_det; ++i) {
+        const int kk = nth_unused(i, d0, d1, d2);
+        const double eu = T1_FMA(-det[2 * kk], az, au), ev = T1_FMA(-det[2 * kk + 1], az, av);
+        maybe = maybe || !(T1_FMA(eu, eu, ev * ev) > lim);
+      }
+    }
+    if (maybe) break;
+  }
+  return maybe;
+}
+
+constexpr int kK2MaxGroup = 8;
+
+template <bool kBBox>
+__global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_t1_kernel(const K2Args a) {
+  const int tid = threadIdx.x;
+  const int n_thr = blockDim.x;
+  const int n_obj = a.pp.n_obj;
+  const int n_perm = n_obj * (n_obj - 1) * (n_obj - 2);
+  const double tol_sq_max = a.pp.back_proj_sq_max;
+  __shared__ double mk[3 * MPE_MAX_LEDS];
+  __shared__ double Ks[9];
+  __shared__ uint2 sq[kK2Survivors];                     // parked problems: (frame, problem index)
+  __shared__ int sq_n;
+  __shared__ int g_frame[kK2MaxGroup], g_ndet[kK2MaxGroup], g_begin[kK2MaxGroup], g_offs[kK2MaxGroup + 1];
+  if (tid < 3 * MPE_MAX_LEDS) mk[tid] = a.pp.markers[tid];
+  if (tid < 9) Ks[tid] = a.cam.K[tid];
+  if (tid == 0) sq_n = 0;
+  __syncthreads();
+  const double* __restrict__ tt = a.triples;
+  const bool listed = a.frame_list != nullptr;
+  const int n_listed = listed ? (int)*a.frame_count : a.n_frames;
+  int split = a.split;
+  const int group = (split > 1) ? 1 : a.group;
+  if (listed && n_listed > 0 && group == 1) { const int s2 = (int)gridDim.x / n_listed; split = max(split, min(16, s2)); }
+  const int n_units = (split > 1) ? n_listed * split : (n_listed + group - 1) / group;
+
+  // exact solve of one parked problem (the reference's arithmetic all the way)
+  auto exact = [&](int f, int t) {
+    const int n_det = a.n_det[f];
+    const int ci = t / n_perm, pj = t - ci * n_perm;
+    const double* cb = a.combos + ((size_t)f * kMaxCombos + ci) * kComboFields;
+    const int ccode = (int)cb[12];
+    int tj = pj;
+    if (ccode & 1) { const int r6 = pj % 6; tj = pj - r6 + ((0x134052 >> (4 * r6)) & 7); }
+    P3PSetup S;
+    S.f_1 = cb[9]; S.f_2 = cb[10]; S.b = cb[11];
+    S.p_1 = tt[(size_t)12 * n_perm + tj]; S.p_2 = tt[(size_t)13 * n_perm + tj]; S.d_12 = tt[(size_t)14 * n_perm + tj];
+    p3p_quartic(S.f_1, S.f_2, S.p_1, S.p_2, S.d_12, S.b, S.roots);
+    asm volatile("" ::: "memory");
+    S.e1 = v_make(cb[0], cb[1], cb[2]); S.e2 = v_make(cb[3], cb[4], cb[5]); S.e3 = v_make(cb[6], cb[7], cb[8]);
+    S.n1 = v_make(tt[tj], tt[(size_t)n_perm + tj], tt[(size_t)2 * n_perm + tj]);
+    S.n2 = v_make(tt[(size_t)3 * n_perm + tj], tt[(size_t)4 * n_perm + tj], tt[(size_t)5 * n_perm + tj]);
+    S.n3 = v_make(tt[(size_t)6 * n_perm + tj], tt[(size_t)7 * n_perm + tj], tt[(size_t)8 * n_perm + tj]);
+    S.P1 = v_make(tt[(size_t)9 * n_perm + tj], tt[(size_t)10 * n_perm + tj], tt[(size_t)11 * n_perm + tj]);
+    const uint32_t ids = ((uint32_t)cb[13] & 0xfffu) | (((uint32_t)tt[(size_t)16 * n_perm + pj] & 0xfffu) << 12);   // d0 d1 d2 | o0 o1 o2 (unswapped row)
+    const double* det = a.det + (size_t)f * a.det_stride * 2;
+    uint32_t* ghist = a.hist + (size_t)f * MPE_MAX_DET * MPE_MAX_LEDS;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      double H[12];
+      if (!p3p_solution(S, k, H)) continue;
+      if (!h_is_finite(H)) continue;                       // pose_estimator.cpp:653
+      score_and_vote(H, ids, n_det, n_obj, det, mk, Ks, tol_sq_max, ghist);
+    }
+  };
+  auto drain = [&](bool all) {                              // called by every thread of the CTA
+    __syncthreads();
+    int n_q = min(sq_n, kK2Survivors);
+    int done = 0;
+    while (n_q - done >= n_thr || (all && done < n_q)) {
+      const int e = done + tid;
+      if (e < n_q) exact((int)sq[e].x, (int)sq[e].y);
+      done += n_thr;
+    }
+    __syncthreads();
+    if (done > 0) {                                         // keep the tail (fewer than a block) for the next round
+      const int rest = max(n_q - done, 0);
+      uint2 keep = make_uint2(0, 0);
+      if (tid < rest) keep = sq[done + tid];
+      __syncthreads();
+      if (tid < rest) sq[tid] = keep;
+      if (tid == 0) sq_n = rest;
+      __syncthreads();
+    }
+  };
+
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    // ---- the frames (or the part of one frame) of this unit
+    if (tid < kK2MaxGroup) {
+      int f = -1, nd = 0, begin = 0, count = 0;
+      if (tid < group) {
+        const int fi = (split > 1) ? unit / split : unit * group + tid;
+        if (fi < n_listed) {
+          f = listed ? a.frame_list[fi] : fi;
+          if (!listed && a.active && !a.active[f]) f = -1;
+        }
+        if (f >= 0) {
+          nd = a.n_det[f];
+          if (nd < 4 || nd > MPE_MAX_DET) { f = -1; nd = 0; }   // pose_estimator.cpp:80; flagged by decode_kernel
+        }
+        if (f >= 0) {
+          const int total = nd * (nd - 1) * (nd - 2) / 6 * n_perm;
+          if (split > 1) {
+            const int part = unit - (unit / split) * split;
+            const int chunk = (total + split - 1) / split;
+            begin = part * chunk;
+            count = max(min(total, begin + chunk) - begin, 0);
+          } else {
+            count = total;
+          }
+        }
+      }
+      g_frame[tid] = f; g_ndet[tid] = nd; g_begin[tid] = begin;
+      g_offs[tid + 1] = count;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      g_offs[0] = 0;
+      for (int g = 0; g < kK2MaxGroup; ++g) g_offs[g + 1] += g_offs[g];
+    }
+    __syncthreads();
+    const int total = g_offs[kK2MaxGroup];
+    const int n_pass = (total + n_thr - 1) / n_thr;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int q = pass * n_thr + tid;
+      if (q < total) {
+        int g = 0;
+#pragma unroll
+        for (int i = 1; i < kK2MaxGroup; ++i) g += (q >= g_offs[i]);
+        const int f = g_frame[g], n_det = g_ndet[g];
+        const int t = g_begin[g] + (q - g_offs[g]);
+        const int ci = t / n_perm, pj = t - ci * n_perm;
+        if (tt[(size_t)15 * n_perm + pj] != 0.0) {            // else: colinear LED triple (tested on the unswapped order, p3p.cpp:77-80)
+          const double* cb = a.combos + ((size_t)f * kMaxCombos + ci) * kComboFields;
+          const int ccode = (int)cb[12];
+          int tj = pj;
+          if (ccode & 1) { const int r6 = pj % 6; tj = pj - r6 + ((0x134052 >> (4 * r6)) & 7); }
+          bool survive = true;
+          if ((ccode & 2) && tt[(size_t)15 * n_perm + tj] == 2.0) {
+            const double* det = a.det + (size_t)f * a.det_stride * 2;
+            double bb[4] = {0, 0, 0, 0};
+            if (kBBox) {                                      // bounding box of the frame's detections
+              double u0 = det[0], u1 = det[0], v0 = det[1], v1 = det[1];
+              for (int i = 1; i < n_det; ++i) { u0 = fmin(u0, det[2 * i]); u1 = fmax(u1, det[2 * i]); v0 = fmin(v0, det[2 * i + 1]); v1 = fmax(v1, det[2 * i + 1]); }
+              bb[0] = 0.5 * (u0 + u1); bb[1] = 0.5 * (v0 + v1);
+              bb[2] = 0.5 * (u1 - u0) * (1.0 + 1e-12) + 1e-9; bb[3] = 0.5 * (v1 - v0) * (1.0 + 1e-12) + 1e-9;
+            }
+            survive = tier1_maybe<kBBox>(cb, tt, n_perm, tj, (uint32_t)cb[13], n_det, n_obj, det, a.filter_r, bb);
+          }
+          if (survive) {
+            const int slot = atomicAdd(&sq_n, 1);
+            if (slot < kK2Survivors) sq[slot] = make_uint2((uint32_t)f, (uint32_t)t);
+            else exact(f, t);                                  // queue full (cannot happen with one drain per pass; kept for safety)
+          }
+        }
+      }
+      // a pass adds at most n_thr entries: drain whenever another pass might not fit
+      __syncthreads();
+      if (sq_n > kK2Survivors - n_thr) drain(false);
+    }
+    __syncthreads();                                           // g_* are rewritten by the next unit
+  }
+  drain(true);
+}
+
 // correspondencesFromHistogram for every frame (one thread each), after the sweep
 __global__ void decode_kernel(const K2Args a) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,7 +680,31 @@ cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st) {
     if (bs < 64) bs = 64;
     if (forced_bs >= 32 && forced_bs <= kK2Threads && forced_bs % 32 == 0) bs = forced_bs;
   }
-  if (a.pp.n_obj >= 7) p3p_sweep_kernel<true><<<grid, bs, 0, st>>>(a);
+  if (a.use_filter == 2) {                                // two-tier sweep: persistent CTAs, `group` frames flattened per unit
+    K2Args b = a;
+    const int n = a.pp.n_obj;
+    const long long per_frame = (long long)n * (n - 1) * (n - 2) / 6 * n * (n - 1) * (n - 2);
+    int group = 1;
+    if (a.split <= 1) {                                   // the group size that fills the passes best (ties: the smaller one)
+      double best = 0;
+      for (int g = 1; g <= kK2MaxGroup; ++g) {
+        const long long tot = per_frame * g;
+        const double fill = (double)tot / (double)((tot + kK2Threads - 1) / kK2Threads * kK2Threads);
+        if (fill > best + 0.02) { best = fill; group = g; }
+      }
+      static int forced_group = -1;
+      if (forced_group < 0) { const char* e = getenv("MPE_K2_GROUP"); forced_group = e ? atoi(e) : 0; }
+      if (forced_group >= 1 && forced_group <= kK2MaxGroup) group = forced_group;
+    }
+    b.group = group;
+    const int units = (a.split > 1) ? a.n_frames * a.split : (a.n_frames + group - 1) / group;
+    int g2 = n_sms * MPE_K2_MINBLOCKS;
+    if (mult > 0) g2 *= mult;
+    if (g2 > units) g2 = units;
+    if (g2 < 1) g2 = 1;
+    if (a.pp.n_obj >= 7) p3p_sweep_t1_kernel<true><<<g2, kK2Threads, 0, st>>>(b);
+    else p3p_sweep_t1_kernel<false><<<g2, kK2Threads, 0, st>>>(b);
+  } else if (a.pp.n_obj >= 7) p3p_sweep_kernel<true><<<grid, bs, 0, st>>>(a);
   else p3p_sweep_kernel<false><<<grid, bs, 0, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

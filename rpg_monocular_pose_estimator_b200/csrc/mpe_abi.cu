@@ -91,7 +91,7 @@ struct mpe_ctx {
   int frame_map_total = 0;
   std::vector<cudaEvent_t> chunk_events;
   // CUDA-graph replay of the tracking step (mpe_streams_step*): the ~30 small launches of one step become one graph launch
-  bool k2_filter = true;                  // K2 conservative reject filter (MPE_K2_NO_FILTER=1 scores every hypothesis exactly)
+  int k2_filter = 2;                      // K2 reject filters: 0 none (every hypothesis scored exactly; MPE_K2_NO_FILTER=1), 1 after the exact solve, 2 tier 1 in front of it
   bool use_graphs = true;
   unsigned long long cfg_version = 0;     // bumped by every configuration call; a stale graph is rebuilt
   struct StepGraphKey {
@@ -335,7 +335,7 @@ int run_sweep(mpe_ctx* c, int slot0, int n, cudaStream_t st, const uint8_t* acti
     const double tol = c->pp.back_projection_pixel_tolerance;
     const double fmax_ = std::fmax(std::fabs(c->cam.K[0]), std::fabs(c->cam.K[4]));
     const double margin = 0.25;
-    k.use_filter = (c->k2_filter && std::isfinite(tol) && tol > 0 && std::isfinite(fmax_) && 4e-6 * fmax_ * 8 <= margin) ? 1 : 0;
+    k.use_filter = (c->k2_filter && std::isfinite(tol) && tol > 0 && std::isfinite(fmax_) && 4e-6 * fmax_ * 8 <= margin) ? c->k2_filter : 0;
     k.filter_r = tol + margin;
   }
   k.corr = c->d.corr + (size_t)slot0 * 2 * MPE_MAX_LEDS;
@@ -514,7 +514,8 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.hist, B * MPE_MAX_DET * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.combos, B * kMaxCombos * kComboFields));
   CREATE_TRY(dev_alloc(&c->d.triples, (size_t)kTripleFields * kMaxPerms));
-  { const char* e = getenv("MPE_K2_NO_FILTER"); c->k2_filter = !(e && e[0] == '1'); }
+  { const char* e = getenv("MPE_K2_NO_FILTER"); if (e && e[0] == '1') c->k2_filter = 0; }
+  { const char* e = getenv("MPE_K2_FILTER"); if (e && e[0] >= '0' && e[0] <= '2') c->k2_filter = e[0] - '0'; }
   CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.n_corr, B));
   CREATE_TRY(dev_alloc(&c->d.pose, B * 16));
@@ -1065,7 +1066,7 @@ int mpe_get_ingest_stats(const mpe_ctx* c, long long* copy_steps, long long* zer
   return MPE_OK;
 }
 
-int mpe_set_k2_filter(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->k2_filter = on != 0; ++c->cfg_version; return MPE_OK; }
+int mpe_set_k2_filter(mpe_ctx* c, int mode) { if (!c) return MPE_E_INVALID; c->k2_filter = (mode == 0) ? 0 : (mode == 1 ? 1 : 2); ++c->cfg_version; return MPE_OK; }
 
 int mpe_set_graph_replay(mpe_ctx* c, int on) { if (!c) return MPE_E_INVALID; c->use_graphs = on != 0; return MPE_OK; }
 

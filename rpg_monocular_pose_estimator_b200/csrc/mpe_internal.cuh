@@ -17,9 +17,11 @@ constexpr int kCandCap = 256;        // candidate contour starts buffered per fr
 constexpr int kMaxFlagWords = 512;   // row-flag words (strips x column tiles) K1b caches per frame; larger geometries are rejected
 constexpr int kMaxCombos = MPE_MAX_DET * (MPE_MAX_DET - 1) * (MPE_MAX_DET - 2) / 6;   // 3-subsets of the detections (560)
 constexpr int kMaxPerms = MPE_MAX_LEDS * (MPE_MAX_LEDS - 1) * (MPE_MAX_LEDS - 2);     // ordered LED triples (3360)
-constexpr int kComboFields = 13;     // K2 detection-triple record (doubles)
-constexpr int kTripleFields = 16;    // K2 LED-triple table fields (doubles)
+constexpr int kComboFields = 23;     // K2 detection-triple record (doubles): frame T, f_1, f_2, b, code, packed indices, K T^T
+constexpr int kTripleXN = 17;        // first field of the unused-LED coordinates in the LED-triple table
+constexpr int kTripleFields = kTripleXN + 3 * (MPE_MAX_LEDS - 3);   // K2 LED-triple table fields (doubles)
 constexpr int kK2Queue = 192;        // hypotheses a K2 CTA can park for exact scoring before it scores in place
+constexpr int kK2Survivors = 768;    // problems a K2 CTA can park between tier 1 and the exact solve
 
 // Camera model as the kernels consume it.
 struct DevCamera {
@@ -108,8 +110,10 @@ struct K2Args {
   uint32_t* hist;            // [n_frames][MPE_MAX_DET*MPE_MAX_LEDS], zeroed before launch
   double* combos;            // [n_frames][kMaxCombos][kComboFields] bearings-only part of every detection triple (prologue kernel)
   const double* triples;     // [kTripleFields][n_perm] LED-triple table (mpe_set_markers)
-  double filter_r;           // back-projection tolerance + margin: radius of the conservative reject filter
-  int use_filter;
+  double filter_r;           // back-projection tolerance + margin: radius of the conservative reject filters
+  int use_filter;            // 0: every hypothesis takes the reference's exact scoring; 1: exact solve + reject filter (round-1 kernel);
+                             // 2: tier 1 in front of the exact solve (p3p_tier1.cuh)
+  int group;                 // frames a CTA flattens into one problem sequence (tier-1 kernel, split == 1)
   uint32_t* corr;            // [n_frames][2*MPE_MAX_LEDS]
   int* n_corr;               // [n_frames]
   int* frame_flags;          // [n_frames] in/out

@@ -1,0 +1,157 @@
+// K2 tier 1 — a cheap, CONSERVATIVE pre-test that runs in front of the exact P3P solve of PoseEstimator::initialise
+// (/root/reference/monocular_pose_estimator_lib/src/pose_estimator.cpp:565-702, p3p.cpp:65-286).
+//
+// About 99 % of the pose hypotheses of the brute-force sweep never vote (no unused detection lies within
+// back_projection_pixel_tolerance_ of the back-projection of an unused LED, :669-676), yet every P3P problem pays for the
+// reference's complex-arithmetic Ferrari quartic (two complex pow, six complex sqrt written after libstdc++/glibc so that
+// the roots are bit-identical) and four back-substitutions.  Tier 1 answers, per problem, "certainly no vote" or "maybe":
+//
+//   1. the quartic's coefficients (p3p.cpp:171-185, any association, FMA allowed) are normalised and depressed;
+//   2. its four roots come from a REAL factorisation into two quadratics  (t^2 + s t + u)(t^2 - s t + v)  through the
+//      largest root z = s^2 of the resolvent cubic  z^3 + 2a z^2 + (a^2 - 4c) z - b^2: float seed from the closed form,
+//      Newton steps in double.  A complex pair contributes its real part twice, which is what the reference uses
+//      (`.real()`, p3p.cpp:276-283);
+//   3. each root rho = cos(theta) with rho^2 <= 1 is back-substituted WITHOUT forming the pose: with
+//      cot(alpha) = num/den the unused LED X (held in the LED triple's frame N, a table) has the camera-frame direction
+//      x_c = T^T v,  v = R' X_N + (d_12 k, 0, 0)  (R' C' collapses to (-d_12 k, 0, 0)), and  K x_c = (K T^T) v  with K T^T a
+//      per-detection-triple table;
+//   4. the division-free test  |a_u - u a_z|^2 + |a_v - v a_z|^2 <= r^2 a_z^2  with r = tolerance + margin against every
+//      unused detection.
+// "maybe" is also the answer whenever the approximation cannot be trusted: ill-conditioned triples (same codes as the exact
+// filter), a (near-)double root, |rho| within 1e-6 of 1, cot(alpha) = 0/0, a point close to the camera plane, a factorisation
+// whose residual is not tiny, or any non-finite intermediate.  Problems answered "maybe" run the unchanged exact path, so the
+// histogram can only differ if tier 1 rejects a problem that the reference would have let vote; the margin (0.25 px by
+// default) is ~1e6 x the deviation between tier-1 and exact back-projections observed on non-flagged problems (measured by
+// tests/test_cpu_k2_tier1.py on the host build of this header and by the on/off histogram tests on the GPU).  This is a
+// validated margin, not a proof: the forward error of the reference's own Ferrari evaluation is covered by the flags above
+// and by measurement.  mpe_set_k2_filter(ctx, 0) switches every filter off (all-exact arm).
+//
+// Host + device: the header also compiles with g++ (tests build it into oracle/libtier1_check.so).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPE_HD __host__ __device__ __forceinline__
+#else
+#define MPE_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define T1_FMA(a, b, c) fma((a), (b), (c))
+#else
+#define T1_FMA(a, b, c) ((a) * (b) + (c))
+#endif
+
+namespace mpe {
+
+constexpr double kT1RootMargin2 = 1e-9;   // rho^2 > 1 + this: sqrt(1 - rho^2) is NaN in the reference as well -> no vote
+constexpr double kT1NearOne = 1e-6;       // 1 - rho^2 below this: sin(theta) is ill-conditioned -> maybe
+constexpr double kT1DiscRel = 1e-6;       // |discriminant| below this fraction of its terms: (near-)double root -> maybe
+constexpr double kT1ResRel = 1e-9;        // factorisation residual |u v - c| relative to the terms -> maybe
+
+struct T1Roots {
+  double rho[4];
+  int n;          // number of values in rho (real roots, and the real part of a complex pair twice)
+  int maybe;      // 1: do not trust (caller must answer "maybe")
+};
+
+// Roots (cos theta) of the P3P quartic for (f_1, f_2, b | p_1, p_2, d_12), p3p.cpp:142-185.
+MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, double p_2, double d_12, T1Roots& R) {
+  R.n = 0; R.maybe = 0;
+  const double F11 = f_1 * f_1, F22 = f_2 * f_2, F12 = f_1 * f_2;
+  const double a = p_1, c = p_2, d = d_12;
+  const double a2 = a * a, c2 = c * c, d2 = d * d, b2 = b * b, ad = a * d;
+  // factors[k] / c^2 (c = p_2 != 0 for a usable triple); same polynomials as p3p.cpp:171-185
+  const double g0 = F22 + F11 + 1.0;
+  const double A = -(c2 * g0);
+  const double B = 2.0 * c * d * (T1_FMA(b, 1.0 + F22, -F12));
+  const double C = T1_FMA(-F22, a2 + d2 * b2 + d2 - c2 - 2.0 * ad, T1_FMA(c2 - a2, F11, T1_FMA(2.0 * ad, 1.0 + F12 * b, -(d2 * b2 + 2.0 * a2))));
+  const double Dq = 2.0 * d * (T1_FMA(a2 - ad, b, c2 * (F12 - F22 * b))) / c;
+  const double E = (T1_FMA(F22 * c2, d2 + a2 + d2 * b2 - 2.0 * ad, T1_FMA(-2.0 * F12 * c2, ad * b, T1_FMA(c2 * F11, a2, a2 * (2.0 * ad - d2 - a2))))) / c2;
+  const double iA = 1.0 / A;
+  const double Bn = B * iA, Cn = C * iA, Dn = Dq * iA, En = E * iA;
+  // depressed quartic t^4 + al t^2 + be t + ga, x = t + sh
+  const double Bn2 = Bn * Bn;
+  const double al = T1_FMA(-0.375, Bn2, Cn);
+  const double be = T1_FMA(Bn, T1_FMA(0.125, Bn2, -0.5 * Cn), Dn);
+  const double ga = T1_FMA(Bn2, T1_FMA(-3.0 / 256.0, Bn2, Cn * (1.0 / 16.0)), T1_FMA(-0.25 * Bn, Dn, En));
+  const double sh = -0.25 * Bn;
+  // resolvent cubic g(z) = z^3 + 2 al z^2 + (al^2 - 4 ga) z - be^2, largest real root (>= 0 because g(0) <= 0)
+  const double c2z = 2.0 * al, c1z = T1_FMA(al, al, -4.0 * ga), c0z = -(be * be);
+  const double pz = T1_FMA(-1.0 / 3.0, c2z * c2z, c1z);
+  const double qz = T1_FMA(c2z, T1_FMA(2.0 / 27.0, c2z * c2z, -(1.0 / 3.0) * c1z), c0z);
+  const double disc = T1_FMA(0.25 * qz, qz, (1.0 / 27.0) * pz * pz * pz);
+  float wseed;
+  if (disc >= 0.0) {
+    const float sq = sqrtf((float)disc);
+    const float hq = (float)(-0.5 * qz);
+    const float big = (hq >= 0.f) ? cbrtf(hq + sq) : cbrtf(hq - sq);
+    wseed = big + ((big != 0.f) ? (float)(-pz / 3.0) / big : 0.f);
+  } else {
+    const float m = 2.f * sqrtf((float)(-pz / 3.0));
+    float arg = (float)(3.0 * qz / pz) / m;
+    arg = fminf(1.f, fmaxf(-1.f, arg));
+    wseed = m * cosf(acosf(arg) * (1.f / 3.f));
+  }
+  double z = (double)wseed - c2z * (1.0 / 3.0);
+  double corr = 0.0;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double g = T1_FMA(T1_FMA(T1_FMA(z, 1.0, c2z), z, c1z), z, c0z);
+    const double gp = T1_FMA(T1_FMA(3.0, z, 2.0 * c2z), z, c1z);
+    corr = g / gp;
+    z -= corr;
+  }
+  if (!(z > 0.0) || !(fabs(corr) <= 1e-9 * z)) { R.maybe = 1; return; }   // also catches NaN, and be == 0 (biquadratic: z may be 0)
+  const double s = sqrt(z);
+  const double bs = be / s;
+  const double u = 0.5 * (al + z - bs), v = 0.5 * (al + z + bs);
+  if (!(fabs(T1_FMA(u, v, -ga)) <= kT1ResRel * (fabs(u * v) + fabs(ga) + z * z))) { R.maybe = 1; return; }
+  const double d1 = T1_FMA(-4.0, u, z), d2q = T1_FMA(-4.0, v, z);
+  if (!(fabs(d1) > kT1DiscRel * (z + 4.0 * fabs(u))) || !(fabs(d2q) > kT1DiscRel * (z + 4.0 * fabs(v)))) { R.maybe = 1; return; }
+  if (d1 >= 0.0) { const double r = sqrt(d1); R.rho[0] = 0.5 * (-s + r) + sh; R.rho[1] = 0.5 * (-s - r) + sh; }
+  else { R.rho[0] = R.rho[1] = -0.5 * s + sh; }
+  if (d2q >= 0.0) { const double r = sqrt(d2q); R.rho[2] = 0.5 * (s + r) + sh; R.rho[3] = 0.5 * (s - r) + sh; }
+  else { R.rho[2] = R.rho[3] = 0.5 * s + sh; }
+  R.n = 4;
+}
+
+// Root-dependent scalars of the back-substitution (p3p.cpp:196-220) without divisions by f_2.
+struct T1Pose {
+  double rho, st;       // cos(theta), sin(theta)
+  double sa, ca;        // sin(alpha), cos(alpha)
+  double dk;            // d_12 * (sin(alpha) b + cos(alpha))
+};
+// returns 0: the reference's hypothesis is NaN (no vote), 1: usable, 2: maybe (ill-conditioned)
+MPE_HD int t1_pose(double rho, double f_1, double f_2, double b, double p_1, double p_2, double d_12, T1Pose& P) {
+  const double om = T1_FMA(-rho, rho, 1.0);
+  if (om < -kT1RootMargin2) return 0;
+  if (!(om >= kT1NearOne)) return 2;
+  // cot(alpha) = num/den, both multiplied by f_2 (the sign of the pair is irrelevant)
+  const double num = T1_FMA(-rho, p_2 * f_2, T1_FMA(d_12 * b, f_2, -(f_1 * p_1)));
+  const double den = T1_FMA(-rho, f_1 * p_2, (p_1 - d_12) * f_2);
+  const double h2 = T1_FMA(num, num, den * den);
+  const double scale = fabs(f_2) * (fabs(p_1) + fabs(p_2) + d_12 * (1.0 + fabs(b))) + fabs(f_1) * (fabs(p_1) + fabs(p_2));
+  if (!(h2 > 1e-16 * scale * scale)) return 2;
+  const double ih = 1.0 / sqrt(h2);
+  P.rho = rho; P.st = sqrt(om);
+  P.sa = fabs(den) * ih;
+  P.ca = ((den >= 0.0) ? num : -num) * ih;
+  P.dk = d_12 * T1_FMA(P.sa, b, P.ca);
+  return 1;
+}
+
+// K x_c (homogeneous pixel coordinates, not normalised) of an LED given in the triple's frame N; Mc = K [e1 e2 e3] (columns).
+MPE_HD void t1_project(const T1Pose& P, const double Mc[9], double X0, double X1, double X2, double& au, double& av, double& az,
+                       double& l1) {
+  const double g = T1_FMA(P.rho, X1, P.st * X2);
+  const double v0 = T1_FMA(-P.ca, X0, T1_FMA(-P.sa, g, P.dk));
+  const double v1 = T1_FMA(P.sa, X0, -(P.ca * g));
+  const double v2 = T1_FMA(-P.st, X1, P.rho * X2);
+  au = T1_FMA(Mc[0], v0, T1_FMA(Mc[1], v1, Mc[2] * v2));
+  av = T1_FMA(Mc[3], v0, T1_FMA(Mc[4], v1, Mc[5] * v2));
+  az = T1_FMA(Mc[6], v0, T1_FMA(Mc[7], v1, Mc[8] * v2));
+  l1 = fabs(v0) + fabs(v1) + fabs(v2);          // |x_c|_1 up to the rotation T (within sqrt(3))
+}
+
+}  // namespace mpe

@@ -190,8 +190,11 @@ class Context:
         self.check(self.L.mpe_get_ingest_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"copy_steps": a.value, "zero_copy_steps": b.value, "h2d_bytes_copied": c.value}
 
-    def set_k2_filter(self, on: bool):
-        self.check(self.L.mpe_set_k2_filter(self.h, 1 if on else 0))
+    def set_k2_filter(self, mode):
+        """0 / False: every hypothesis of the sweep is scored exactly; 1: reject filter behind the exact P3P solve;
+        2 / True (default): tier-1 pre-test in front of it (csrc/p3p_tier1.cuh).  Results are identical in all modes."""
+        m = 2 if mode is True else (0 if mode is False else int(mode))
+        self.check(self.L.mpe_set_k2_filter(self.h, m))
 
     def set_graph_replay(self, on: bool):
         self.check(self.L.mpe_set_graph_replay(self.h, 1 if on else 0))

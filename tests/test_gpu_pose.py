@@ -200,11 +200,14 @@ def test_sweep_reject_filter_never_changes_a_vote(gpu_ctx_752):
                     if rep % 3 == 2:                          # ... or the view plus a detection one pixel next to another
                         det = np.vstack([det, det[0] + [1.0, 0.0]])
                     det = np.ascontiguousarray(det[rng.permutation(len(det))])
-                    ctx.set_k2_filter(True)
+                    ctx.set_k2_filter(2)
                     h_on = _hist(ctx, det)
-                    ctx.set_k2_filter(False)
+                    ctx.set_k2_filter(1)
+                    h_on1 = _hist(ctx, det)
+                    ctx.set_k2_filter(0)
                     h_off = _hist(ctx, det)
                     assert np.array_equal(h_on, h_off), (n_leds, tol, rep, h_on, h_off)
+                    assert np.array_equal(h_on1, h_off), (n_leds, tol, rep, h_on1, h_off)
                     n_cases += 1; n_votes += int(h_on.sum())
                     if rep == 0 and tol == 5.0:
                         est = pose_oracle.PoseEstimatorOracle(K, D, mk, p)
