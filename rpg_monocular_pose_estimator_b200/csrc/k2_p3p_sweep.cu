@@ -429,30 +429,42 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
 // accumulated — across frames: the CTA is persistent — every thread takes one and runs the reference's arithmetic
 // (p3p_quartic, four back-substitutions, exact scoring).  A CTA flattens `group` consecutive frames into one problem sequence
 // so that its passes are full (600 problems of one 5-LED frame fill 2.3 passes of 256 threads, 1200 of two fill 4.7).
-template <bool kBBox>
+// kNuObj = n_obj - 3 when that is 1..3 (coordinates of the unused LEDs held in registers, loops unrolled), 0 = any number.
+// `sdet` = the frame's detections in shared memory, `dlist` = the indices of the unused detections (4 bits each).
+template <int kNuObj, bool kBBox>
 __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const double* __restrict__ tt, int n_perm, int tj,
-                                            uint32_t ids, int n_det, int n_obj, const double* __restrict__ det, double r, const double bb[4]) {
+                                            unsigned long long dlist, int nu_det, int nu_obj_rt, const double2* __restrict__ sdet,
+                                            double r, const double bb[4]) {
   T1Roots R;
   const double f_1 = cb[9], f_2 = cb[10], b = cb[11];
-  const double p_1 = tt[(size_t)12 * n_perm + tj], p_2 = tt[(size_t)13 * n_perm + tj], d_12 = tt[(size_t)14 * n_perm + tj];
+  const double* __restrict__ tr = tt + tj;                  // field k of this row: tr[k * n_perm]
+  const double p_1 = tr[12 * n_perm], p_2 = tr[13 * n_perm], d_12 = tr[14 * n_perm];
   t1_quartic_roots(f_1, f_2, b, p_1, p_2, d_12, R);
   if (R.maybe) return true;
-  const int d0 = ids & 15, d1 = (ids >> 4) & 15, d2 = (ids >> 8) & 15;
-  const int nu_obj = n_obj - 3, nu_det = n_det - 3;
+  const int nu_obj = (kNuObj > 0) ? kNuObj : nu_obj_rt;
   const double r2 = r * r;
   double Mc[9];
 #pragma unroll
   for (int e = 0; e < 9; ++e) Mc[e] = cb[14 + e];
+  double X[(kNuObj > 0) ? kNuObj : 1][3];
+  if (kNuObj > 0) {
+#pragma unroll
+    for (int m = 0; m < kNuObj; ++m)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) X[m][q] = tr[(kTripleXN + 3 * m + q) * n_perm];
+  }
   bool maybe = false;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     T1Pose P;
     const int st = t1_pose(R.rho[k], f_1, f_2, b, p_1, p_2, d_12, P);
     if (st == 0) continue;
-    if (st == 2) { maybe = true; break; }
+    if (st == 2) return true;
+#pragma unroll
     for (int m = 0; m < nu_obj; ++m) {
-      const double X0 = tt[(size_t)(kTripleXN + 3 * m) * n_perm + tj], X1 = tt[(size_t)(kTripleXN + 3 * m + 1) * n_perm + tj],
-                   X2 = tt[(size_t)(kTripleXN + 3 * m + 2) * n_perm + tj];
+      double X0, X1, X2;
+      if (kNuObj > 0) { X0 = X[m][0]; X1 = X[m][1]; X2 = X[m][2]; }
+      else { X0 = tr[(kTripleXN + 3 * m) * n_perm]; X1 = tr[(kTripleXN + 3 * m + 1) * n_perm]; X2 = tr[(kTripleXN + 3 * m + 2) * n_perm]; }
       double au, av, az, l1;
       t1_project(P, Mc, X0, X1, X2, au, av, az, l1);
       // close to the camera plane (or to the camera itself): the division-free comparison is not trusted
@@ -464,15 +476,16 @@ __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const
         if (outside && !near_plane) continue;
       }
       const double lim = r2 * (az * az);
-      for (int i = 0; i < nu_det; ++i) {
-        const int kk = nth_unused(i, d0, d1, d2);
-        const double eu = T1_FMA(-det[2 * kk], az, au), ev = T1_FMA(-det[2 * kk + 1], az, av);
+      unsigned long long dl = dlist;
+      for (int i = 0; i < nu_det; ++i, dl >>= 4) {
+        const double2 d = sdet[(int)(dl & 15ull)];
+        const double eu = T1_FMA(-d.x, az, au), ev = T1_FMA(-d.y, az, av);
         maybe = maybe || !(T1_FMA(eu, eu, ev * ev) > lim);
       }
     }
-    if (maybe) break;
+    if (maybe) return true;
   }
-  return maybe;
+  return false;
 }
 
 constexpr int kK2MaxGroup = 8;
@@ -483,12 +496,15 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_t1_ker
   const int n_thr = blockDim.x;
   const int n_obj = a.pp.n_obj;
   const int n_perm = n_obj * (n_obj - 1) * (n_obj - 2);
+  const float inv_perm = 1.0f / (float)n_perm;
   const double tol_sq_max = a.pp.back_proj_sq_max;
   __shared__ double mk[3 * MPE_MAX_LEDS];
   __shared__ double Ks[9];
   __shared__ uint2 sq[kK2Survivors];                     // parked problems: (frame, problem index)
   __shared__ int sq_n;
   __shared__ int g_frame[kK2MaxGroup], g_ndet[kK2MaxGroup], g_begin[kK2MaxGroup], g_offs[kK2MaxGroup + 1];
+  __shared__ double2 g_det[kK2MaxGroup][MPE_MAX_DET];    // the detections of the unit's frames
+  __shared__ double g_bb[kK2MaxGroup][4];
   if (tid < 3 * MPE_MAX_LEDS) mk[tid] = a.pp.markers[tid];
   if (tid < 9) Ks[tid] = a.cam.K[tid];
   if (tid == 0) sq_n = 0;
@@ -575,6 +591,15 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_t1_ker
           } else {
             count = total;
           }
+          const double* det = a.det + (size_t)f * a.det_stride * 2;
+          double u0 = det[0], u1 = det[0], v0 = det[1], v1 = det[1];
+          for (int i = 0; i < nd; ++i) {
+            const double u = det[2 * i], v = det[2 * i + 1];
+            g_det[tid][i] = make_double2(u, v);
+            u0 = fmin(u0, u); u1 = fmax(u1, u); v0 = fmin(v0, v); v1 = fmax(v1, v);
+          }
+          g_bb[tid][0] = 0.5 * (u0 + u1); g_bb[tid][1] = 0.5 * (v0 + v1);           // bounding box of the detections
+          g_bb[tid][2] = 0.5 * (u1 - u0) * (1.0 + 1e-12) + 1e-9; g_bb[tid][3] = 0.5 * (v1 - v0) * (1.0 + 1e-12) + 1e-9;
         }
       }
       g_frame[tid] = f; g_ndet[tid] = nd; g_begin[tid] = begin;
@@ -592,27 +617,33 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_t1_ker
       const int q = pass * n_thr + tid;
       if (q < total) {
         int g = 0;
+        if (group > 1) {
 #pragma unroll
-        for (int i = 1; i < kK2MaxGroup; ++i) g += (q >= g_offs[i]);
+          for (int i = 1; i < kK2MaxGroup; ++i) g += (q >= g_offs[i]);
+        }
         const int f = g_frame[g], n_det = g_ndet[g];
         const int t = g_begin[g] + (q - g_offs[g]);
-        const int ci = t / n_perm, pj = t - ci * n_perm;
-        if (tt[(size_t)15 * n_perm + pj] != 0.0) {            // else: colinear LED triple (tested on the unswapped order, p3p.cpp:77-80)
-          const double* cb = a.combos + ((size_t)f * kMaxCombos + ci) * kComboFields;
+        int ci = (int)((float)t * inv_perm);                  // t / n_perm (t < 2^21: the float quotient is off by at most one)
+        int pj = t - ci * n_perm;
+        if (pj < 0) { --ci; pj += n_perm; } else if (pj >= n_perm) { ++ci; pj -= n_perm; }
+        const double* __restrict__ cb = a.combos + ((size_t)f * kMaxCombos + ci) * kComboFields;
+        if (tt[15 * n_perm + pj] != 0.0) {                    // else: colinear LED triple (tested on the unswapped order, p3p.cpp:77-80)
           const int ccode = (int)cb[12];
           int tj = pj;
           if (ccode & 1) { const int r6 = pj % 6; tj = pj - r6 + ((0x134052 >> (4 * r6)) & 7); }
           bool survive = true;
-          if ((ccode & 2) && tt[(size_t)15 * n_perm + tj] == 2.0) {
-            const double* det = a.det + (size_t)f * a.det_stride * 2;
-            double bb[4] = {0, 0, 0, 0};
-            if (kBBox) {                                      // bounding box of the frame's detections
-              double u0 = det[0], u1 = det[0], v0 = det[1], v1 = det[1];
-              for (int i = 1; i < n_det; ++i) { u0 = fmin(u0, det[2 * i]); u1 = fmax(u1, det[2 * i]); v0 = fmin(v0, det[2 * i + 1]); v1 = fmax(v1, det[2 * i + 1]); }
-              bb[0] = 0.5 * (u0 + u1); bb[1] = 0.5 * (v0 + v1);
-              bb[2] = 0.5 * (u1 - u0) * (1.0 + 1e-12) + 1e-9; bb[3] = 0.5 * (v1 - v0) * (1.0 + 1e-12) + 1e-9;
-            }
-            survive = tier1_maybe<kBBox>(cb, tt, n_perm, tj, (uint32_t)cb[13], n_det, n_obj, det, a.filter_r, bb);
+          if ((ccode & 2) && tt[15 * n_perm + tj] == 2.0) {
+            const uint32_t dd = (uint32_t)cb[13];
+            const int d0 = dd & 15, d1 = (dd >> 4) & 15, d2 = (dd >> 8) & 15;
+            const int nu_det = n_det - 3;
+            unsigned long long dlist = 0;
+            for (int i = 0; i < nu_det; ++i) dlist |= (unsigned long long)nth_unused(i, d0, d1, d2) << (4 * i);
+            const double* bb = g_bb[g];
+            const int nuo = n_obj - 3;
+            if (nuo == 1) survive = tier1_maybe<1, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
+            else if (nuo == 2) survive = tier1_maybe<2, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
+            else if (nuo == 3) survive = tier1_maybe<3, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
+            else survive = tier1_maybe<0, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
           }
           if (survive) {
             const int slot = atomicAdd(&sq_n, 1);

@@ -17,9 +17,14 @@
 //      per-detection-triple table;
 //   4. the division-free test  |a_u - u a_z|^2 + |a_v - v a_z|^2 <= r^2 a_z^2  with r = tolerance + margin against every
 //      unused detection.
-// "maybe" is also the answer whenever the approximation cannot be trusted: ill-conditioned triples (same codes as the exact
-// filter), a (near-)double root, |rho| within 1e-6 of 1, cot(alpha) = 0/0, a point close to the camera plane, a factorisation
-// whose residual is not tiny, or any non-finite intermediate.  Problems answered "maybe" run the unchanged exact path, so the
+// Tier 1 computes ACCURATE roots; the reference's Ferrari evaluation does not always (its R = -Q/2 + sqrt(Q^2/4 + P^3/27) cancels
+// for Q > 0, and its 2 beta / w is 0/0-like for a nearly biquadratic quartic), and what votes is what the reference computes.
+// So "maybe" is also the answer whenever the two can drift apart or the approximation cannot be trusted: more than five
+// digits cancelled in R (kT1Cancel), w^2 tiny (kT1SmallW), a pair of roots closer than 1e-3 (real pair or complex pair is then
+// a matter of rounding), ill-conditioned triples (same codes as the exact filter), 1 - rho^2 below 1e-4, cot(alpha) = 0/0,
+// a point close to the camera plane, a factorisation whose residual is not tiny, or any non-finite intermediate.  With these
+// flags the largest |rho_tier1 - rho_reference| over 1e7 unflagged hypotheses is 7.5e-9 (1e-5 px), and every deviation above
+// 1e-9 found without them is explained by one of the three indicators (tests/test_cpu_k2_tier1.py prints the statistics).  Problems answered "maybe" run the unchanged exact path, so the
 // histogram can only differ if tier 1 rejects a problem that the reference would have let vote; the margin (0.25 px by
 // default) is ~1e6 x the deviation between tier-1 and exact back-projections observed on non-flagged problems (measured by
 // tests/test_cpu_k2_tier1.py on the host build of this header and by the on/off histogram tests on the GPU).  This is a
@@ -45,9 +50,19 @@
 namespace mpe {
 
 constexpr double kT1RootMargin2 = 1e-9;   // rho^2 > 1 + this: sqrt(1 - rho^2) is NaN in the reference as well -> no vote
-constexpr double kT1NearOne = 1e-6;       // 1 - rho^2 below this: sin(theta) is ill-conditioned -> maybe
-constexpr double kT1DiscRel = 1e-6;       // |discriminant| below this fraction of its terms: (near-)double root -> maybe
+constexpr double kT1NearOne = 1e-4;       // 1 - rho^2 below this: sin(theta) is ill-conditioned -> maybe
+constexpr double kT1PairSep = 1e-3;       // two roots closer than this (in cos theta): real pair or complex pair is a matter of rounding -> maybe
+#ifndef MPE_T1_CANCEL
+#define MPE_T1_CANCEL 1e5
+#endif
+constexpr double kT1Cancel = MPE_T1_CANCEL;         // Q/2 over |R| in the reference's Ferrari step: more cancellation than this -> maybe
+constexpr double kT1SmallW = 1e-5;        // w^2 = z below this fraction of |alpha| + sqrt|gamma|: the reference divides 2 beta by a w that is mostly rounding -> maybe
 constexpr double kT1ResRel = 1e-9;        // factorisation residual |u v - c| relative to the terms -> maybe
+
+#ifdef MPE_T1_DEBUG
+struct T1Debug { double al, be, ga, z, kappa, d1, d2; };
+static T1Debug g_t1_debug;
+#endif
 
 struct T1Roots {
   double rho[4];
@@ -81,6 +96,20 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
   const double pz = T1_FMA(-1.0 / 3.0, c2z * c2z, c1z);
   const double qz = T1_FMA(c2z, T1_FMA(2.0 / 27.0, c2z * c2z, -(1.0 / 3.0) * c1z), c0z);
   const double disc = T1_FMA(0.25 * qz, qz, (1.0 / 27.0) * pz * pz * pz);
+  // The reference's Ferrari evaluation forms R = -Q/2 + sqrt(Q^2/4 + P^3/27) (p3p.cpp:262; here qz = 8Q, pz = 4P, disc = 64 times
+  // the radicand): for Q > 0 the two terms cancel and the roots it RETURNS drift away from the true roots of the quartic by
+  // the lost digits.  Tier 1 computes accurate roots, so it stands back when more than kT1CancelDigits are lost.
+#ifdef MPE_T1_DEBUG
+  g_t1_debug.al = al; g_t1_debug.be = be; g_t1_debug.ga = ga; g_t1_debug.kappa = 0; g_t1_debug.z = 0; g_t1_debug.d1 = g_t1_debug.d2 = 0;
+#endif
+  if (qz > 0.0 && disc > 0.0) {
+    const double sq = sqrt(disc);
+    const double Rq = ((1.0 / 27.0) * pz * pz * pz) / (sq + 0.5 * qz);       // = sqrt(disc) - qz/2 without the cancellation
+#ifdef MPE_T1_DEBUG
+    g_t1_debug.kappa = 0.5 * qz / fabs(Rq);
+#endif
+    if (!(fabs(Rq) * kT1Cancel >= 0.5 * qz)) { R.maybe = 1; return; }
+  }
   float wseed;
   if (disc >= 0.0) {
     const float sq = sqrtf((float)disc);
@@ -102,13 +131,16 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
     corr = g / gp;
     z -= corr;
   }
-  if (!(z > 0.0) || !(fabs(corr) <= 1e-9 * z)) { R.maybe = 1; return; }   // also catches NaN, and be == 0 (biquadratic: z may be 0)
+  if (!(z > kT1SmallW * (fabs(al) + sqrt(fabs(ga)))) || !(fabs(corr) <= 1e-9 * z)) { R.maybe = 1; return; }   // also catches NaN, and be == 0 (biquadratic: z may be 0)
   const double s = sqrt(z);
   const double bs = be / s;
   const double u = 0.5 * (al + z - bs), v = 0.5 * (al + z + bs);
   if (!(fabs(T1_FMA(u, v, -ga)) <= kT1ResRel * (fabs(u * v) + fabs(ga) + z * z))) { R.maybe = 1; return; }
   const double d1 = T1_FMA(-4.0, u, z), d2q = T1_FMA(-4.0, v, z);
-  if (!(fabs(d1) > kT1DiscRel * (z + 4.0 * fabs(u))) || !(fabs(d2q) > kT1DiscRel * (z + 4.0 * fabs(v)))) { R.maybe = 1; return; }
+#ifdef MPE_T1_DEBUG
+  g_t1_debug.z = z; g_t1_debug.d1 = d1; g_t1_debug.d2 = d2q;
+#endif
+  if (!(fabs(d1) > kT1PairSep * kT1PairSep) || !(fabs(d2q) > kT1PairSep * kT1PairSep)) { R.maybe = 1; return; }   // separation = sqrt(|disc|)
   if (d1 >= 0.0) { const double r = sqrt(d1); R.rho[0] = 0.5 * (-s + r) + sh; R.rho[1] = 0.5 * (-s - r) + sh; }
   else { R.rho[0] = R.rho[1] = -0.5 * s + sh; }
   if (d2q >= 0.0) { const double r = sqrt(d2q); R.rho[2] = 0.5 * (s + r) + sh; R.rho[3] = 0.5 * (s - r) + sh; }
