@@ -27,18 +27,34 @@
 #include "../mpe_b200.h"
 
 #if !defined(MPE_SHIM_FORCE_STANDIN) && defined(__has_include)
-#if __has_include(<Eigen/Dense>) && __has_include(<opencv2/core.hpp>)
+#if __has_include(<Eigen/Dense>) && (__has_include(<opencv2/core.hpp>) || __has_include(<opencv2/opencv.hpp>))
 #define MPE_SHIM_REAL_TYPES 1
 #endif
 #endif
 
 #ifdef MPE_SHIM_REAL_TYPES
 #include <Eigen/Dense>
+#if __has_include(<opencv2/core.hpp>)
 #include <opencv2/core.hpp>
+#else
+#include <opencv2/opencv.hpp>
+#endif
 namespace monocular_pose_estimator {
+// datatypes.h:38-52 (all of them, so that sources written against the reference's header compile unchanged) + led_detector.h:39
 typedef Eigen::Matrix<double, 6, 6> Matrix6d;
+typedef Eigen::Matrix<double, 2, 6> Matrix2x6d;
+typedef Eigen::Matrix<double, 3, 4> Matrix3x4d;
+typedef Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic> MatrixXYd;
+typedef Eigen::Matrix<unsigned, Eigen::Dynamic, Eigen::Dynamic> MatrixXYu;
+typedef Eigen::Matrix<double, 6, 1> Vector6d;
+typedef Eigen::Matrix<unsigned, 3, 1> Vector3u;
+typedef Eigen::Matrix<unsigned, 4, 1> Vector4u;
+typedef Eigen::Matrix<unsigned, Eigen::Dynamic, 1> VectorXu;
 typedef Eigen::Matrix<unsigned, Eigen::Dynamic, 2> VectorXuPairs;
+typedef Eigen::Matrix<double, 1, Eigen::Dynamic> RowXd;
+typedef Eigen::Matrix<unsigned, 1, Eigen::Dynamic> RowXu;
 typedef Eigen::Matrix<Eigen::Vector2d, Eigen::Dynamic, 1> List2DPoints;
+typedef Eigen::Matrix<Eigen::Vector3d, Eigen::Dynamic, 1> List3DPoints;
 typedef Eigen::Matrix<Eigen::Vector4d, Eigen::Dynamic, 1> List4DPoints;
 typedef Eigen::Matrix4d Matrix4dT;
 typedef cv::Mat ImageT;
@@ -70,6 +86,14 @@ template <int R, int C> struct Mat {   // column-major like Eigen
   double& operator()(int r, int c) { return m[c * R + r]; }
   double operator()(int r, int c) const { return m[c * R + r]; }
 };
+template <int N> struct UVec { unsigned v[N]; UVec() { for (int i = 0; i < N; ++i) v[i] = 0; } unsigned& operator()(int i) { return v[i]; } unsigned operator()(int i) const { return v[i]; } };
+template <typename T> struct DynMat {   // column-major like Eigen
+  std::vector<T> d; int r = 0, c = 0;
+  int rows() const { return r; } int cols() const { return c; }
+  void resize(int rows, int cols) { r = rows; c = cols; d.assign((size_t)rows * cols, T()); }
+  T& operator()(int i, int j) { return d[(size_t)j * r + i]; }
+  const T& operator()(int i, int j) const { return d[(size_t)j * r + i]; }
+};
 struct Pairs {
   std::vector<unsigned> d; int n = 0;
   int rows() const { return n; }
@@ -84,9 +108,20 @@ struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w)
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
 }  // namespace standin
 typedef standin::Mat<6, 6> Matrix6d;
+typedef standin::Mat<2, 6> Matrix2x6d;
+typedef standin::Mat<3, 4> Matrix3x4d;
+typedef standin::Vec<6> Vector6d;
 typedef standin::Pairs VectorXuPairs;
 typedef standin::List<standin::Vec<2> > List2DPoints;
+typedef standin::List<standin::Vec<3> > List3DPoints;
 typedef standin::List<standin::Vec<4> > List4DPoints;
+typedef standin::List<double> RowXd;
+typedef standin::List<unsigned> RowXu;
+typedef standin::List<unsigned> VectorXu;
+typedef standin::UVec<3> Vector3u;
+typedef standin::UVec<4> Vector4u;
+typedef standin::DynMat<double> MatrixXYd;
+typedef standin::DynMat<unsigned> MatrixXYu;
 typedef standin::Mat<4, 4> Matrix4dT;
 typedef standin::Image ImageT;
 typedef standin::Camera CameraMatT;
@@ -105,19 +140,6 @@ inline void check(mpe_ctx* c, int rc, const char* what) {
 }
 inline void camera_to_rowmajor(const CameraMatT& K, double out[9]) {
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[3 * r + c] = cam_at(K, r, c);
-}
-// small row-major 4x4 helpers for the host-side tracking math
-inline void mul44(const double* A, const double* B, double* C) {
-  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j]; C[4 * i + j] = s; }
-}
-inline void rigid_inverse(const double* T, double* Ti) {   // general inverse of [R t; 0 1] through the 3x3 adjugate
-  const double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];
-  const double A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
-  const double det = a * A + b * B + c * Cc, id = 1.0 / det;
-  double Ri[9] = {A * id, -(b * i - c * h) * id, (b * f - c * e) * id, B * id, (a * i - c * g) * id, -(a * f - c * d) * id,
-                  Cc * id, -(a * h - b * g) * id, (a * e - b * d) * id};
-  for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) Ti[4 * r + cc] = Ri[3 * r + cc]; Ti[4 * r + 3] = -(Ri[3 * r] * T[3] + Ri[3 * r + 1] * T[7] + Ri[3 * r + 2] * T[11]); }
-  Ti[12] = Ti[13] = Ti[14] = 0; Ti[15] = 1;
 }
 }  // namespace detail
 
@@ -152,40 +174,16 @@ class LEDDetector {
     }
   }
 
-  // led_detector.cpp:181-224
-  static void distortPoints(const std::vector<Point2fT>& src, std::vector<Point2fT>& dst, const CameraMatT& K, const std::vector<double>& D) {
-    dst.clear();
-    const double fx = cam_at(K, 0, 0), fy = cam_at(K, 1, 1), cx = cam_at(K, 0, 2), cy = cam_at(K, 1, 2);
-    const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
-    for (size_t i = 0; i < src.size(); ++i) {
-      const double x = ((double)src[i].x - cx) / fx, y = ((double)src[i].y - cy) / fy;
-      const double r2 = x * x + y * y;
-      double xc = x * (1. + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2), yc = y * (1. + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2);
-      xc = xc + (2. * p1 * x * y + p2 * (r2 + 2. * x * x));
-      yc = yc + (p1 * (r2 + 2. * y * y) + 2. * p2 * x * y);
-      dst.push_back(Point2fT((float)(xc * fx + cx), (float)(yc * fy + cy)));
-    }
-  }
-
-  // led_detector.cpp:114-179
+  // led_detector.cpp:114-179 with distortPoints :181-224 — computed by the library's host helper, the very function the device
+  // loop runs per stream (csrc/tracking_math.cuh), so stage mode and device loop cannot drift apart
   static RectT determineROI(List2DPoints pixel_positions, SizeT image_size, const int border_size, const CameraMatT& K, const std::vector<double>& D) {
-    double x_min = INFINITY, x_max = 0, y_min = INFINITY, y_max = 0;
-    for (unsigned i = 0; i < pixel_positions.size(); ++i) {
-      if (pixel_positions(i)(0) < x_min) x_min = pixel_positions(i)(0);
-      if (pixel_positions(i)(0) > x_max) x_max = pixel_positions(i)(0);
-      if (pixel_positions(i)(1) < y_min) y_min = pixel_positions(i)(1);
-      if (pixel_positions(i)(1) > y_max) y_max = pixel_positions(i)(1);
-    }
-    std::vector<Point2fT> und, dis;
-    und.push_back(Point2fT((float)x_min, (float)y_min));
-    und.push_back(Point2fT((float)x_max, (float)y_max));
-    distortPoints(und, dis, K, D);
-    const double x0 = std::max(0.0, std::min((double)image_size.width, (double)dis[0].x - border_size));
-    const double x1 = std::max(0.0, std::min((double)image_size.width, (double)dis[1].x + border_size));
-    const double y0 = std::max(0.0, std::min((double)image_size.height, (double)dis[0].y - border_size));
-    const double y1 = std::max(0.0, std::min((double)image_size.height, (double)dis[1].y + border_size));
-    if (x1 - x0 < 1 || y1 - y0 < 1) return RectT(0, 0, image_size.width, image_size.height);
-    return RectT((int)x0, (int)y0, (int)(x1 - x0), (int)(y1 - y0));
+    std::vector<double> px(2 * (size_t)pixel_positions.size());
+    for (unsigned i = 0; i < pixel_positions.size(); ++i) { px[2 * i] = pixel_positions(i)(0); px[2 * i + 1] = pixel_positions(i)(1); }
+    double Kr[9]; detail::camera_to_rowmajor(K, Kr);
+    mpe_rect r;
+    detail::check(nullptr, mpe_host_determine_roi(px.data(), (int)pixel_positions.size(), image_size.width, image_size.height, border_size, Kr,
+                                                  D.data(), (int)D.size(), &r), "mpe_host_determine_roi");
+    return RectT(r.x, r.y, r.width, r.height);
   }
 
  private:
@@ -229,6 +227,8 @@ class PoseEstimator {
     markers_dirty_ = true;
   }
   List4DPoints getMarkerPositions() { return object_points_; }
+  // pose_estimator.cpp:44-48 forwards to Visualization::createVisualizationImage (debug overlay, out of scope): the image is left as is
+  void augmentImage(ImageT& /*image*/) {}
   void setPredictedPose(const Matrix4dT& pose, double time) { fromEigen(pose, predicted_pose_); predicted_time_ = time; }
   Matrix4dT getPredictedPose() { return toEigen(predicted_pose_); }
   Matrix6d getPoseCovariance() { Matrix6d c; for (int r = 0; r < 6; ++r) for (int q = 0; q < 6; ++q) c(r, q) = cov_[6 * r + q]; return c; }
@@ -263,7 +263,7 @@ class PoseEstimator {
 
   // pose_estimator.cpp:62-147
   bool estimateBodyPose(ImageT image, double time_to_predict) {
-    pose_updated_ = false;
+    pose_updated_ = false; too_many_detections_ = false;
     ensureContext(image.cols, image.rows);
     push();   // the caller may have changed the public fields since the last frame
     if (device_loop_) return estimateBodyPoseOnDevice(image, time_to_predict);
@@ -303,6 +303,7 @@ class PoseEstimator {
     detail::check(ctx_, mpe_streams_step(ctx_, image.data, (int)(size_t)image.step, (long long)image.step * image.rows, image.cols, image.rows, 1,
                                          &time_to_predict, &r), "mpe_streams_step");
     predicted_time_ = time_to_predict;
+    too_many_detections_ = (r.flags & MPE_F_TOO_MANY_DET) != 0;
     region_of_interest_ = RectT(r.roi.x, r.roi.y, r.roi.width, r.roi.height);
     const int nd = r.n_det < MPE_MAX_DET ? r.n_det : MPE_MAX_DET;
     if (nd > 0) {                                                               // pixel_positions untouched when nothing was found (led_detector.cpp:91)
@@ -329,6 +330,7 @@ class PoseEstimator {
 
   unsigned initialise() {                                                       // :544-721 (K2 + K3a + Kabsch)
     push();
+    if (image_points_.size() > (size_t)MPE_MAX_DET) { too_many_detections_ = true; return 0; }   // capacity of the sweep's tables: no pose, no exception
     std::vector<double> det; flatten(image_points_, det);
     uint32_t corr[2 * MPE_MAX_LEDS]; int k = 0, ok = 0; double pose[16];
     detail::check(ctx_, mpe_initialise(ctx_, det.data(), (int)image_points_.size(), nullptr, corr, &k, pose, &ok), "mpe_initialise");
@@ -340,6 +342,7 @@ class PoseEstimator {
   unsigned checkCorrespondences() {                                             // :394-542
     push();
     if (correspondences_.rows() < 4) return 0;
+    if (image_points_.size() > (size_t)MPE_MAX_DET) { compactToMatchedDetections(); if (image_points_.size() < 4) return 0; }
     std::vector<double> det; flatten(image_points_, det);
     std::vector<uint32_t> corr; flattenCorr(corr);
     int ok = 0; double pose[16];
@@ -376,15 +379,13 @@ class PoseEstimator {
     if (checkCorrespondences() == 1) optimiseAndUpdatePose(time_to_predict);
     else if (initialise() == 1) optimiseAndUpdatePose(time_to_predict);
   }
-  void predictMarkerPositionsInImage() {                                        // :270-276 with project2d :251-268
+  void predictMarkerPositionsInImage() {                                        // :270-276 with project2d :251-268 ((K|0)*T first)
     predicted_pixel_positions_.resize(object_points_.size());
     double K[9]; detail::camera_to_rowmajor(camera_matrix_K_, K);
-    for (unsigned i = 0; i < object_points_.size(); ++i) {
-      double p[4] = {object_points_(i)(0), object_points_(i)(1), object_points_(i)(2), object_points_(i)(3)}, c[3], t[3];
-      for (int r = 0; r < 3; ++r) c[r] = predicted_pose_[4 * r] * p[0] + predicted_pose_[4 * r + 1] * p[1] + predicted_pose_[4 * r + 2] * p[2] + predicted_pose_[4 * r + 3] * p[3];
-      for (int r = 0; r < 3; ++r) t[r] = K[3 * r] * c[0] + K[3 * r + 1] * c[1] + K[3 * r + 2] * c[2];
-      predicted_pixel_positions_(i)(0) = t[0] / t[2]; predicted_pixel_positions_(i)(1) = t[1] / t[2];
-    }
+    std::vector<double> xyz(3 * (size_t)object_points_.size()), px(2 * (size_t)object_points_.size());
+    for (unsigned i = 0; i < object_points_.size(); ++i) for (int k = 0; k < 3; ++k) xyz[3 * i + k] = object_points_(i)(k);
+    detail::check(ctx_, mpe_host_project_markers(K, predicted_pose_, xyz.data(), (int)object_points_.size(), px.data()), "mpe_host_project_markers");
+    for (unsigned i = 0; i < object_points_.size(); ++i) { predicted_pixel_positions_(i)(0) = px[2 * i]; predicted_pixel_positions_(i)(1) = px[2 * i + 1]; }
   }
   void findCorrespondences() {                                                  // :372-392 (+ :862-906)
     std::vector<unsigned> rows;
@@ -399,55 +400,31 @@ class PoseEstimator {
     }
     correspondences_.resize((int)rows.size() / 2, 2);
     for (size_t i = 0; i < rows.size() / 2; ++i) { correspondences_((int)i, 0) = rows[2 * i]; correspondences_((int)i, 1) = rows[2 * i + 1]; }
+    if (image_points_.size() > (size_t)MPE_MAX_DET) compactToMatchedDetections();
   }
-  void predictPose(double time_to_predict) {                                    // :232-244
+  // Capacity path, same as the device loop (csrc/k4_tracking.cu): the brute-force tables hold MPE_MAX_DET detections; with more,
+  // the detections that are some LED's nearest neighbour are compacted to the front (ascending) and the rows renumbered.
+  void compactToMatchedDetections() {
+    std::vector<int> remap(image_points_.size(), 0);
+    for (int r = 0; r < correspondences_.rows(); ++r) remap[correspondences_(r, 1) - 1] = 1;
+    List2DPoints kept; kept.resize(image_points_.size());
+    size_t m = 0;
+    for (size_t j = 0; j < image_points_.size(); ++j) if (remap[j]) { kept(m) = image_points_(j); remap[j] = (int)++m; }
+    List2DPoints out; out.resize(m);
+    for (size_t j = 0; j < m; ++j) out(j) = kept(j);
+    image_points_ = out;
+    for (int r = 0; r < correspondences_.rows(); ++r) correspondences_(r, 1) = (unsigned)remap[correspondences_(r, 1) - 1];
+    too_many_detections_ = true;
+  }
+  bool tooManyDetections() const { return too_many_detections_; }
+  void predictPose(double time_to_predict) {                                    // :232-244 (general 4x4 inverse, log map, exp map)
     predicted_time_ = time_to_predict;
-    double inv[16], rel[16], delta[6], delta_hat[6], E[16], out[16];
-    detail::rigid_inverse(previous_pose_, inv);
-    detail::mul44(inv, current_pose_, rel);
-    logarithmMap(rel, delta);
-    for (int i = 0; i < 6; ++i) delta_hat[i] = delta[i] / (current_time_ - previous_time_) * (predicted_time_ - current_time_);
-    exponentialMap(delta_hat, E);
-    detail::mul44(current_pose_, E, out);
+    double out[16];
+    detail::check(ctx_, mpe_host_predict_pose(previous_pose_, current_pose_, previous_time_, current_time_, time_to_predict, out), "mpe_host_predict_pose");
     std::memcpy(predicted_pose_, out, sizeof(out));
   }
-
-  static void exponentialMap(const double twist[6], double T[16]) {             // :962-994
-    const double wx = twist[3], wy = twist[4], wz = twist[5];
-    const double th = std::sqrt(wx * wx + wy * wy + wz * wz), th2 = th * th;
-    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-    double O2[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
-    double R[9], V[9];
-    for (int i = 0; i < 9; ++i) {
-      const double I = (i % 4 == 0) ? 1.0 : 0.0;
-      if (th == 0) { R[i] = I; V[i] = I; }
-      else { R[i] = I + O[i] / th * std::sin(th) + O2[i] / th2 * (1 - std::cos(th)); V[i] = I + (1 - std::cos(th)) / th2 * O[i] + (th - std::sin(th)) / (th2 * th) * O2[i]; }
-    }
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c]; T[4 * r + 3] = V[3 * r] * twist[0] + V[3 * r + 1] * twist[1] + V[3 * r + 2] * twist[2]; }
-    T[12] = T[13] = T[14] = 0; T[15] = 1;
-  }
-  static void logarithmMap(const double T[16], double xi[6]) {                  // :996-1064
-    double R[9], t[3]; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[3 * r + c] = T[4 * r + c]; t[r] = T[4 * r + 3]; }
-    double w_hat[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double dn = 0, rn = 0; for (int i = 0; i < 9; ++i) { const double I = (i % 4 == 0) ? 1.0 : 0.0; dn += (R[i] - I) * (R[i] - I); rn += R[i] * R[i]; }
-    if (!(dn <= 1e-20 * std::min(rn, 3.0))) {
-      double temp = (R[0] + R[4] + R[8] - 1) / 2; if (temp > 1) temp = 1; else if (temp < -1) temp = -1;
-      const double phi = std::acos(temp);
-      if (phi != 0) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) w_hat[3 * r + c] = (R[3 * r + c] - R[3 * c + r]) / (2 * std::sin(phi)) * phi;
-    }
-    const double w[3] = {w_hat[7], w_hat[2], w_hat[3]};
-    const double wn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    double A[9];
-    if (t[0] == 0 && t[1] == 0 && t[2] == 0) { for (int i = 0; i < 9; ++i) A[i] = 0; }
-    else if (wn == 0 || std::sin(wn) == 0) { for (int i = 0; i < 9; ++i) A[i] = (i % 4 == 0) ? 1.0 : 0.0; }
-    else {
-      const double k = (2 * std::sin(wn) - wn * (1 + std::cos(wn))) / (2 * wn * wn * std::sin(wn));
-      double w2[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w2[3 * i + j] = w_hat[3 * i] * w_hat[j] + w_hat[3 * i + 1] * w_hat[3 + j] + w_hat[3 * i + 2] * w_hat[6 + j];
-      for (int i = 0; i < 9; ++i) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - w_hat[i] / 2 + k * w2[i];
-    }
-    for (int r = 0; r < 3; ++r) xi[r] = A[3 * r] * t[0] + A[3 * r + 1] * t[1] + A[3 * r + 2] * t[2];
-    xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];
-  }
+  static void exponentialMap(const double twist[6], double T[16]) { mpe_host_exponential_map(twist, T); }   // :962-994
+  static void logarithmMap(const double T[16], double xi[6]) { mpe_host_logarithm_map(T, xi); }             // :996-1064
 
   const RectT& regionOfInterest() const { return region_of_interest_; }
   const double* predictedPoseRowMajor() const { return predicted_pose_; }
@@ -501,7 +478,7 @@ class PoseEstimator {
   }
 
   mpe_ctx* ctx_; int ctx_w_, ctx_h_; bool markers_dirty_ = true;
-  bool device_loop_ = true, pushed_valid_ = false;
+  bool device_loop_ = true, pushed_valid_ = false, too_many_detections_ = false;
   mpe_params pushed_params_; double pushed_K_[9]; std::vector<double> pushed_D_; unsigned pushed_hist_ = 0;
   double current_pose_[16], previous_pose_[16], predicted_pose_[16], cov_[36];   // row-major
   double current_time_, previous_time_, predicted_time_;

@@ -165,6 +165,28 @@ int mpe_synchronize(mpe_ctx* ctx);
 /* Copies the n poses (row-major 4x4, 16 doubles each) of the last batch into a DEVICE buffer on the context's
  * stream — the record a multi-GPU caller all-gathers over NCCL. */
 int mpe_copy_poses_device(mpe_ctx* ctx, int n_frames, double* poses_device);
+/* The same for the complete mpe_result records of the last batch / tracking step (n x sizeof(mpe_result) bytes). */
+int mpe_copy_results_device(mpe_ctx* ctx, int n_frames, mpe_result* results_device);
+/* Host-side helpers of tracking mode (no context, no GPU).  The device loop (mpe_streams_step*) runs these functions per
+ * stream on the GPU; callers that drive the stages themselves — PoseEstimator::predictPose / predictMarkerPositionsInImage /
+ * predictWithROI of the C++ shim and of the Python mirror — get the same arithmetic here, in the reference's operation order:
+ * predictPose (pose_estimator.cpp:232-244: general 4x4 inverse, logarithmMap :996-1064, exponentialMap :962-994),
+ * project2d ((K|0)*T first, then the point; :251-268), LEDDetector::determineROI with distortPoints (led_detector.cpp:114-224).
+ * Poses are row-major 4x4, pixels n x 2, markers n x 3. */
+int mpe_host_predict_pose(const double previous_pose[16], const double current_pose[16], double previous_time, double current_time,
+                          double time_to_predict, double predicted_pose_out[16]);
+int mpe_host_project_markers(const double K[9], const double pose[16], const double* markers_xyz, int n, double* pixels_out);
+int mpe_host_determine_roi(const double* pixels, int n, int width, int height, int border, const double K[9], const double* D, int nD,
+                           mpe_rect* roi_out);
+int mpe_host_exponential_map(const double twist[6], double pose_out[16]);
+int mpe_host_logarithm_map(const double pose[16], double twist_out[6]);
+/* Debug aid, host only (no context, no GPU): the 8-bit fixed-point Gaussian taps (sum 256) that mpe_set_params derives from
+ * gaussian_sigma — OpenCV's bit-exact kernel for CV_8U with ksize = (0,0) (led_detector.cpp:48-51).  MPE_E_INVALID when the
+ * radius would exceed 18 (sigma > ~6.08), MPE_E_CAPACITY when taps_out is too small. */
+int mpe_debug_gaussian_taps(double sigma, int* radius_out, uint32_t* taps_out, int taps_capacity);
+/* Measurement aid: FP64 throughput of this device (TFLOP/s, FMA = 2) from a kernel of independent DFMA chains — the
+ * denominator of the K2 / K3 FP64 roofline in bench.py (MEASURED_PEAKS.json holds no FP64 figure). */
+int mpe_probe_fp64_peak(mpe_ctx* ctx, double* tflops_out);
 
 /* Tracking mode: S independent streams, each a PoseEstimator with device-resident state
  * (current/previous/predicted pose, times, it_since_initialized_).  One call advances every stream by
@@ -211,10 +233,12 @@ int mpe_get_ingest_stats(const mpe_ctx* ctx, long long* copy_steps, long long* z
  * [4] blur_tiles (K1c, exact fixed-point blur of the hot tiles). */
 int mpe_enable_kernel_timing(mpe_ctx* ctx, int on);
 int mpe_get_kernel_times(mpe_ctx* ctx, float ms_out[5]);
-/* The brute-force sweep of initialise() rejects most pose hypotheses with a conservative, division-free projection test before
- * the reference's exact scoring (results are identical by construction).  0 switches the test off, so that
- * every finite hypothesis goes through the exact arithmetic — for A/B verification. */
-int mpe_set_k2_filter(mpe_ctx* ctx, int on);
+/* The brute-force sweep of initialise() (pose_estimator.cpp:565-702) spends its time on hypotheses that never vote.  mode 2
+ * (default): a cheap conservative pre-test (csrc/p3p_tier1.cuh) runs in front of the exact P3P solve and only the problems it
+ * cannot rule out take the reference's arithmetic; mode 1: every problem is solved exactly and a conservative projection test
+ * precedes the exact scoring (the round-1 kernel); mode 0: every finite hypothesis goes through the exact scoring — the
+ * all-exact arm for A/B verification.  The histogram is the same in all modes (tests compare them). */
+int mpe_set_k2_filter(mpe_ctx* ctx, int mode);
 /* number of kernel launches issued by this context so far */
 long long mpe_kernel_launch_count(const mpe_ctx* ctx);
 

@@ -81,6 +81,70 @@ def lib():
     return _LIB
 
 
+_CLIB = None
+
+
+class _Counted:
+    """libpose_oracle_counted.so (the restatement compiled on a counting double, oracle/counted_double.h) under the mpeo_* names."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        if name.startswith("mpeo_"):
+            return getattr(self._L, "mpeoc_" + name[len("mpeo_"):])
+        return getattr(self._L, name)
+
+
+def counted_lib():
+    global _CLIB
+    if _CLIB is None:
+        so = os.path.join(_HERE, "libpose_oracle_counted.so")
+        src = [os.path.join(_HERE, n) for n in ("pose_oracle.cpp", "pose_oracle_counted.cpp", "counted_double.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in src):
+            subprocess.check_call(["make", "-C", _HERE, "libpose_oracle_counted.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.mpeoc_create.restype = C.c_void_p
+        for name, args, res in SIGNATURES:
+            fn = getattr(L, "mpeoc_" + name[len("mpeo_"):])
+            fn.argtypes = args
+            fn.restype = res
+        L.mpeoc_ops_get.argtypes = [C.POINTER(C.c_ulonglong)]
+        _CLIB = L
+    return _CLIB
+
+
+OP_CLASSES = ("add", "mul", "div", "sqrt", "cmp", "special")
+
+
+def count_ops(K, D, markers, params, detections):
+    """Exact FP64 operation counts of the CPU restatement for one frame's pose path, per stage:
+    {'initialise': {...}, 'optimise': {...}} with the classes of OP_CLASSES plus 'flops' = add + mul + div + sqrt + cmp
+    (transcendental library calls are listed separately as 'special').  `initialise` = setImagePoints + the brute-force
+    sweep + histogram decode + checkCorrespondences (pose_estimator.cpp:544-721), `optimise` = optimisePose (:733-792)."""
+    L = counted_lib()
+    est = PoseEstimatorOracle(K, D, markers, params, _lib=_Counted(L))
+
+    def read():
+        out = (C.c_ulonglong * 6)()
+        L.mpeoc_ops_get(out)
+        d = dict(zip(OP_CLASSES, [int(v) for v in out]))
+        d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"] + d["cmp"]
+        return d
+
+    L.mpeoc_ops_reset()
+    est.set_image_points(detections)
+    ok = est.initialise()
+    init = read()
+    opt = None
+    if ok:
+        L.mpeoc_ops_reset()
+        iters = est.optimise_pose()
+        opt = read()
+        opt["gn_iterations"] = iters
+    return {"ok": ok, "initialise": init, "optimise": opt, "histogram": est.histogram(), "correspondences": est.correspondences()}
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "mpe_set_histogram_threshold", "mpe_get_histogram_threshold", "mpe_find_leds", "mpe_initialise",
     "mpe_check_correspondences", "mpe_optimise_pose", "mpe_p3p_compute_poses", "mpe_estimate_batch",
     "mpe_estimate_batch_device", "mpe_estimate_batch_device_async", "mpe_fetch_results", "mpe_synchronize", "mpe_copy_poses_device",
-    "mpe_streams_reset", "mpe_streams_set_frame_map", "mpe_streams_step_device", "mpe_streams_step", "mpe_set_graph_replay", "mpe_set_ingest_mode", "mpe_get_ingest_stats", "mpe_set_k2_filter",
+    "mpe_streams_reset", "mpe_streams_set_frame_map", "mpe_streams_step_device", "mpe_streams_step", "mpe_set_graph_replay", "mpe_set_ingest_mode", "mpe_get_ingest_stats", "mpe_set_k2_filter", "mpe_copy_results_device", "mpe_probe_fp64_peak", "mpe_debug_gaussian_taps", "mpe_host_predict_pose", "mpe_host_project_markers", "mpe_host_determine_roi", "mpe_host_exponential_map", "mpe_host_logarithm_map",
     "mpe_enable_kernel_timing", "mpe_get_kernel_times",
     "mpe_kernel_launch_count", "mpe_pose_to_message",
 ]
@@ -95,6 +95,14 @@ def load_library():
         "mpe_set_graph_replay": ([vp, C.c_int], C.c_int),
         "mpe_set_ingest_mode": ([vp, C.c_int], C.c_int),
         "mpe_set_k2_filter": ([vp, C.c_int], C.c_int),
+        "mpe_copy_results_device": ([vp, C.c_int, vp], C.c_int),
+        "mpe_probe_fp64_peak": ([vp, C.POINTER(C.c_double)], C.c_int),
+        "mpe_host_predict_pose": ([dp, dp, C.c_double, C.c_double, C.c_double, dp], C.c_int),
+        "mpe_host_project_markers": ([dp, dp, dp, C.c_int, dp], C.c_int),
+        "mpe_host_determine_roi": ([dp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.POINTER(MpeRect)], C.c_int),
+        "mpe_host_exponential_map": ([dp, dp], C.c_int),
+        "mpe_host_logarithm_map": ([dp, dp], C.c_int),
+        "mpe_debug_gaussian_taps": ([C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_int], C.c_int),
         "mpe_get_ingest_stats": ([vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)], C.c_int),
         "mpe_enable_kernel_timing": ([vp, C.c_int], C.c_int),
         "mpe_get_kernel_times": ([vp, fp], C.c_int),

@@ -480,11 +480,10 @@ template <bool kLow, int kStages>
 static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
   size_t smem = find_leds_smem_bytes(a.g, a.radius, kStages);
   auto kern = scan_kernel<kLow, kStages>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrCache configured;
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, smem, configured, 0);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   int n_tiles = a.g.n_frames * a.g.n_strips * a.g.n_ct;
   // CTAs per SM: two for the ~100 KB rings of whole-image rows; up to four (the register limit: 256 threads x 60 registers) for the
@@ -950,13 +949,12 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extr
 
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
   int grid = (a.g.n_frames + kBlobWarpsPerCta - 1) / kBlobWarpsPerCta;
-  static size_t configured = 0;
+  static SmemAttrCache configured;
   const int flags_cap = a.g.flags_per_frame < kMaxFlagWords ? a.g.flags_per_frame : kMaxFlagWords;
   size_t smem = k1b_scratch_stride(flags_cap, a.g.mask_rows) * kBlobWarpsPerCta;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(extract_blobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dynamic_smem(extract_blobs_kernel, smem, configured);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, smem, st>>>(a);
   return cudaGetLastError();

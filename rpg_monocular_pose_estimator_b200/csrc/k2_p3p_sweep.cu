@@ -30,6 +30,12 @@ namespace mpe {
 #ifndef MPE_K2_MINBLOCKS
 #define MPE_K2_MINBLOCKS 3
 #endif
+#ifndef MPE_T1_UNROLL_K
+#define MPE_T1_UNROLL_K 0   // 1: the four roots of tier 1 unrolled (more registers; measured slower at 80 registers)
+#endif
+#ifndef MPE_T1_DET_REGS
+#define MPE_T1_DET_REGS 1   // 1: unused detections in registers when n_det == n_obj
+#endif
 constexpr int kK2Threads = MPE_K2_THREADS;
 
 // lexicographic unranking of a 3-combination of {0..n-1}
@@ -429,11 +435,12 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_kernel
 // accumulated — across frames: the CTA is persistent — every thread takes one and runs the reference's arithmetic
 // (p3p_quartic, four back-substitutions, exact scoring).  A CTA flattens `group` consecutive frames into one problem sequence
 // so that its passes are full (600 problems of one 5-LED frame fill 2.3 passes of 256 threads, 1200 of two fill 4.7).
-// kNuObj = n_obj - 3 when that is 1..3 (coordinates of the unused LEDs held in registers, loops unrolled), 0 = any number.
-// `sdet` = the frame's detections in shared memory, `dlist` = the indices of the unused detections (4 bits each).
-template <int kNuObj, bool kBBox>
+// kNuObj = number of unused LEDs (n_obj - 3) when it is compiled in (loops unrolled), 0 = any number; kNuDet likewise for the
+// unused detections; kXRegs: the unused LEDs' coordinates are held in registers (few LEDs) instead of being re-read from the
+// table.  `sdet` = the frame's detections in shared memory, `dlist` = the indices of the unused detections (4 bits each).
+template <int kNuObj, int kNuDet, bool kXRegs, bool kBBox>
 __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const double* __restrict__ tt, int n_perm, int tj,
-                                            unsigned long long dlist, int nu_det, int nu_obj_rt, const double2* __restrict__ sdet,
+                                            unsigned long long dlist, int nu_det_rt, int nu_obj_rt, const double2* __restrict__ sdet,
                                             double r, const double bb[4]) {
   T1Roots R;
   const double f_1 = cb[9], f_2 = cb[10], b = cb[11];
@@ -442,48 +449,67 @@ __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const
   t1_quartic_roots(f_1, f_2, b, p_1, p_2, d_12, R);
   if (R.maybe) return true;
   const int nu_obj = (kNuObj > 0) ? kNuObj : nu_obj_rt;
+  const int nu_det = (kNuDet > 0) ? kNuDet : nu_det_rt;
   const double r2 = r * r;
   double Mc[9];
 #pragma unroll
   for (int e = 0; e < 9; ++e) Mc[e] = cb[14 + e];
-  double X[(kNuObj > 0) ? kNuObj : 1][3];
-  if (kNuObj > 0) {
+  double X[kXRegs ? kNuObj : 1][3];
+  if (kXRegs) {
 #pragma unroll
     for (int m = 0; m < kNuObj; ++m)
 #pragma unroll
       for (int q = 0; q < 3; ++q) X[m][q] = tr[(kTripleXN + 3 * m + q) * n_perm];
   }
+  double2 dreg[(kNuDet > 0) ? kNuDet : 1];
+  if (kNuDet > 0) {
+#pragma unroll
+    for (int i = 0; i < kNuDet; ++i) dreg[i] = sdet[(int)((dlist >> (4 * i)) & 15ull)];
+  }
   bool maybe = false;
+#if MPE_T1_UNROLL_K
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int k = 0; k < 4; ++k) {
     T1Pose P;
     const int st = t1_pose(R.rho[k], f_1, f_2, b, p_1, p_2, d_12, P);
-    if (st == 0) continue;
     if (st == 2) return true;
+    if (st == 1) {
 #pragma unroll
-    for (int m = 0; m < nu_obj; ++m) {
-      double X0, X1, X2;
-      if (kNuObj > 0) { X0 = X[m][0]; X1 = X[m][1]; X2 = X[m][2]; }
-      else { X0 = tr[(kTripleXN + 3 * m) * n_perm]; X1 = tr[(kTripleXN + 3 * m + 1) * n_perm]; X2 = tr[(kTripleXN + 3 * m + 2) * n_perm]; }
-      double au, av, az, l1;
-      t1_project(P, Mc, X0, X1, X2, au, av, az, l1);
-      // close to the camera plane (or to the camera itself): the division-free comparison is not trusted
-      const bool near_plane = !(fabs(az) >= 1e-3 * l1) || !(l1 >= 1e-3 * d_12);
-      maybe = maybe || near_plane;
-      if (kBBox) {
-        const double aaz = fabs(az);
-        const bool outside = fabs(au - bb[0] * az) > (bb[2] + r) * aaz || fabs(av - bb[1] * az) > (bb[3] + r) * aaz;
-        if (outside && !near_plane) continue;
+      for (int m = 0; m < nu_obj; ++m) {
+        double X0, X1, X2;
+        if (kXRegs) { X0 = X[m][0]; X1 = X[m][1]; X2 = X[m][2]; }
+        else { X0 = tr[(kTripleXN + 3 * m) * n_perm]; X1 = tr[(kTripleXN + 3 * m + 1) * n_perm]; X2 = tr[(kTripleXN + 3 * m + 2) * n_perm]; }
+        double au, av, az, l1;
+        t1_project(P, Mc, X0, X1, X2, au, av, az, l1);
+        // close to the camera plane (or to the camera itself): the division-free comparison is not trusted
+        const bool near_plane = !(fabs(az) >= 1e-3 * l1) || !(l1 >= 1e-3 * d_12);
+        maybe = maybe || near_plane;
+        if (kBBox) {
+          const double aaz = fabs(az);
+          const bool outside = fabs(au - bb[0] * az) > (bb[2] + r) * aaz || fabs(av - bb[1] * az) > (bb[3] + r) * aaz;
+          if (outside && !near_plane) continue;
+        }
+        const double lim = r2 * (az * az);
+        if (kNuDet > 0) {
+#pragma unroll
+          for (int i = 0; i < kNuDet; ++i) {
+            const double eu = T1_FMA(-dreg[i].x, az, au), ev = T1_FMA(-dreg[i].y, az, av);
+            maybe = maybe || !(T1_FMA(eu, eu, ev * ev) > lim);
+          }
+        } else {
+          unsigned long long dl = dlist;
+          for (int i = 0; i < nu_det; ++i, dl >>= 4) {
+            const double2 d = sdet[(int)(dl & 15ull)];
+            const double eu = T1_FMA(-d.x, az, au), ev = T1_FMA(-d.y, az, av);
+            maybe = maybe || !(T1_FMA(eu, eu, ev * ev) > lim);
+          }
+        }
       }
-      const double lim = r2 * (az * az);
-      unsigned long long dl = dlist;
-      for (int i = 0; i < nu_det; ++i, dl >>= 4) {
-        const double2 d = sdet[(int)(dl & 15ull)];
-        const double eu = T1_FMA(-d.x, az, au), ev = T1_FMA(-d.y, az, av);
-        maybe = maybe || !(T1_FMA(eu, eu, ev * ev) > lim);
-      }
+      if (maybe) return true;
     }
-    if (maybe) return true;
   }
   return false;
 }
@@ -640,10 +666,16 @@ __global__ void __launch_bounds__(kK2Threads, MPE_K2_MINBLOCKS) p3p_sweep_t1_ker
             for (int i = 0; i < nu_det; ++i) dlist |= (unsigned long long)nth_unused(i, d0, d1, d2) << (4 * i);
             const double* bb = g_bb[g];
             const int nuo = n_obj - 3;
-            if (nuo == 1) survive = tier1_maybe<1, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
-            else if (nuo == 2) survive = tier1_maybe<2, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
-            else if (nuo == 3) survive = tier1_maybe<3, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
-            else survive = tier1_maybe<0, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, g_det[g], a.filter_r, bb);
+            const double r = a.filter_r;
+            const double2* sd = g_det[g];
+            if (nuo == 1) survive = (MPE_T1_DET_REGS && nu_det == 1) ? tier1_maybe<1, 1, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb)
+                                                  : tier1_maybe<1, 0, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb);
+            else if (nuo == 2) survive = (MPE_T1_DET_REGS && nu_det == 2) ? tier1_maybe<2, 2, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb)
+                                                       : tier1_maybe<2, 0, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb);
+            else if (nuo == 3) survive = (MPE_T1_DET_REGS && nu_det == 3) ? tier1_maybe<3, 3, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb)
+                                                       : tier1_maybe<3, 0, true, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb);
+            else if (nuo == 5) survive = tier1_maybe<5, 0, false, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb);
+            else survive = tier1_maybe<0, 0, false, kBBox>(cb, tt, n_perm, tj, dlist, nu_det, nuo, sd, r, bb);
           }
           if (survive) {
             const int slot = atomicAdd(&sq_n, 1);

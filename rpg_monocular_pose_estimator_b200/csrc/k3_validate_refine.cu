@@ -1052,11 +1052,10 @@ cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
     int G = (Nmax <= kK3aThreads) ? kK3aThreads / Nmax : 1;
     if (G > 32) G = 32;
     size_t smem = (size_t)G * sizeof(CheckFrame) + (size_t)kK3aThreads * n_obj * 3 * sizeof(double) + kK3aThreads * sizeof(int);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemAttrCache configured;
+    {
+      cudaError_t e = ensure_dynamic_smem(check_kernel, smem, configured);
       if (e != cudaSuccess) return e;
-      configured = smem;
     }
     int grid = (a.n_frames + G - 1) / G;
     check_kernel<<<grid, kK3aThreads, smem, st>>>(a, G, Nmax);

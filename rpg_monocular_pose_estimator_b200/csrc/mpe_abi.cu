@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "mpe_internal.cuh"
+#include "tracking_math.cuh"
 
 using namespace mpe;
 
@@ -128,12 +129,17 @@ int fail(mpe_ctx* c, int code, const std::string& msg) {
 
 // OpenCV getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED for CV_8U (ksize from sigma:
 // cvRound(sigma*6+1)|1), 8 fractional bits, centre tap = 256 - sum(others).  Verified against cv2 4.13
-// impulse responses and full-image blurs for sigma in [0.3, 6] (tests/test_blur_model.py).
+// impulse responses and full-image blurs for sigma in [0.3, 6] (tests/test_cpu_gaussian_taps.py sweeps sigma on the CPU through mpe_debug_gaussian_taps, tests/test_gpu_find_leds.py compares whole frames).
 bool gaussian_taps_8u(double sigma, int* radius, uint32_t taps[kMaxTaps]) {
   if (!(sigma > 0)) return false;
   int n = (int)std::nearbyint(sigma * 6 + 1) | 1;
   int n2 = (n - 1) / 2;
-  if (n2 < 1 || n2 > kMaxRadius) return false;
+  if (n2 > kMaxRadius) return false;
+  if (n2 < 1) {            // sigma < 1/12: OpenCV's kernel has one tap, the blur is the identity; same as radius 1 with taps 0 256 0
+    taps[0] = 0; taps[1] = 256; taps[2] = 0;
+    *radius = 1;
+    return true;
+  }
   std::vector<double> vals(n2);
   double scale2x = -0.5 / (sigma * sigma);
   double sum = 0;
@@ -770,21 +776,22 @@ int mpe_p3p_compute_poses(mpe_ctx* c, const double* feature_vectors, const doubl
   if (!c || n < 0 || (n > 0 && (!feature_vectors || !world_points || !solutions || !status))) return MPE_E_INVALID;
   if (n == 0) return MPE_OK;
   CUDA_TRY(c, cudaSetDevice(c->device));
-  double *df = nullptr, *dP = nullptr, *ds = nullptr;
-  int* dst = nullptr;
   cudaStream_t st = c->stream;
-  CUDA_TRY(c, cudaMalloc((void**)&df, (size_t)n * 9 * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc((void**)&dP, (size_t)n * 9 * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc((void**)&ds, (size_t)n * 48 * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc((void**)&dst, (size_t)n * sizeof(int)));
-  CUDA_TRY(c, cudaMemcpyAsync(df, feature_vectors, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(c, cudaMemcpyAsync(dP, world_points, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  // one allocation for the four arrays, released on every path (doubles first: alignment)
+  struct Scratch { void* p = nullptr; ~Scratch() { if (p) cudaFree(p); } } scratch;
+  const size_t nf = (size_t)n * 9, ns = (size_t)n * 48;
+  CUDA_TRY(c, cudaMalloc(&scratch.p, (2 * nf + ns) * sizeof(double) + (size_t)n * sizeof(int)));
+  double* df = (double*)scratch.p;
+  double* dP = df + nf;
+  double* ds = dP + nf;
+  int* dst = (int*)(ds + ns);
+  CUDA_TRY(c, cudaMemcpyAsync(df, feature_vectors, nf * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(dP, world_points, nf * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(c, launch_p3p_batch(df, dP, n, ds, dst, st));
   ++c->launches;
-  CUDA_TRY(c, cudaMemcpyAsync(solutions, ds, (size_t)n * 48 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(solutions, ds, ns * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaMemcpyAsync(status, dst, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaStreamSynchronize(st));
-  cudaFree(df); cudaFree(dP); cudaFree(ds); cudaFree(dst);
   return MPE_OK;
 }
 
@@ -864,6 +871,111 @@ int mpe_copy_poses_device(mpe_ctx* c, int n_frames, double* poses_device) {
   if (!c || !poses_device || n_frames < 1 || n_frames > c->max_batch) return MPE_E_INVALID;
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaMemcpyAsync(poses_device, c->d.pose, (size_t)n_frames * 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return MPE_OK;
+}
+
+// ---- host-side helpers of the stage-by-stage mirrors (no context, no GPU): the same functions K4 runs per stream ------------
+namespace {
+mpe::DevCamera host_camera(const double K[9], const double* D, int nD) {
+  mpe::DevCamera cam; std::memset(&cam, 0, sizeof(cam));
+  for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
+  for (int i = 0; i < nD && i < MPE_MAX_DIST; ++i) cam.D[i] = D[i];
+  cam.nD = nD;
+  return cam;
+}
+mpe::M4 m4_of(const double* p) { mpe::M4 m; std::memcpy(m.m, p, sizeof(m.m)); return m; }
+}  // namespace
+
+int mpe_host_predict_pose(const double previous_pose[16], const double current_pose[16], double previous_time, double current_time,
+                          double time_to_predict, double predicted_pose_out[16]) {
+  if (!previous_pose || !current_pose || !predicted_pose_out) return MPE_E_INVALID;
+  const mpe::M4 r = mpe::predict_pose(m4_of(previous_pose), m4_of(current_pose), previous_time, current_time, time_to_predict);
+  std::memcpy(predicted_pose_out, r.m, sizeof(r.m));
+  return MPE_OK;
+}
+int mpe_host_project_markers(const double K[9], const double pose[16], const double* markers_xyz, int n, double* pixels_out) {
+  if (!K || !pose || !markers_xyz || !pixels_out || n < 0) return MPE_E_INVALID;
+  const mpe::M4 T = m4_of(pose);
+  for (int i = 0; i < n; ++i) mpe::project2d(K, T, markers_xyz[3 * i], markers_xyz[3 * i + 1], markers_xyz[3 * i + 2], pixels_out[2 * i], pixels_out[2 * i + 1]);
+  return MPE_OK;
+}
+int mpe_host_determine_roi(const double* pixels, int n, int width, int height, int border, const double K[9], const double* D, int nD, mpe_rect* roi_out) {
+  if (!pixels || !K || !roi_out || n < 0 || nD < 0 || (nD > 0 && !D)) return MPE_E_INVALID;
+  const mpe::Roi r = mpe::determine_roi(host_camera(K, D, nD), pixels, n, width, height, border);
+  roi_out->x = r.x; roi_out->y = r.y; roi_out->width = r.w; roi_out->height = r.h;
+  return MPE_OK;
+}
+int mpe_host_exponential_map(const double twist[6], double pose_out[16]) {
+  if (!twist || !pose_out) return MPE_E_INVALID;
+  const mpe::M4 r = mpe::exponential_map(twist);
+  std::memcpy(pose_out, r.m, sizeof(r.m));
+  return MPE_OK;
+}
+int mpe_host_logarithm_map(const double pose[16], double twist_out[6]) {
+  if (!pose || !twist_out) return MPE_E_INVALID;
+  mpe::logarithm_map(m4_of(pose), twist_out);
+  return MPE_OK;
+}
+
+// host-only debug export: the fixed-point Gaussian taps mpe_set_params derives from sigma (no context, no GPU)
+int mpe_debug_gaussian_taps(double sigma, int* radius_out, uint32_t* taps_out, int taps_capacity) {
+  if (!radius_out || !taps_out) return MPE_E_INVALID;
+  uint32_t taps[kMaxTaps];
+  int r = 0;
+  if (!gaussian_taps_8u(sigma, &r, taps)) return MPE_E_INVALID;
+  if (2 * r + 1 > taps_capacity) return MPE_E_CAPACITY;
+  for (int i = 0; i < 2 * r + 1; ++i) taps_out[i] = taps[i];
+  *radius_out = r;
+  return MPE_OK;
+}
+
+int mpe_copy_results_device(mpe_ctx* c, int n_frames, mpe_result* results_device) {
+  if (!c || !results_device || n_frames < 1 || n_frames > c->max_batch) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpyAsync(results_device, c->d.results, (size_t)n_frames * sizeof(mpe_result), cudaMemcpyDeviceToDevice, c->stream));
+  return MPE_OK;
+}
+
+// FP64 peak probe: kProbeChains independent DFMA chains per thread, enough CTAs to fill every SM.
+namespace {
+constexpr int kProbeChains = 8, kProbeIters = 4096;
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, double a, double b) {
+  double x[kProbeChains];
+#pragma unroll
+  for (int i = 0; i < kProbeChains; ++i) x[i] = a + (double)(threadIdx.x + i);
+  for (int it = 0; it < kProbeIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < kProbeChains; ++i) x[i] = fma(x[i], b, a);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < kProbeChains; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;          // never true: keeps the chains alive
+}
+}  // namespace
+
+int mpe_probe_fp64_peak(mpe_ctx* c, double* tflops_out) {
+  if (!c || !tflops_out) return MPE_E_INVALID;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  double* d = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int grid = c->n_sms * 8;
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    fp64_probe_kernel<<<grid, 256, 0, c->stream>>>(d, 0.5, 0.999999);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(c, MPE_E_CUDA, std::string("fp64 probe: ") + cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * (double)grid * 256.0 * kProbeChains * kProbeIters;
+    if (rep > 0 && ms > 0) best = std::fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops_out = best;
   return MPE_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/mpe_b200.h"
 
 namespace mpe {
@@ -22,6 +23,27 @@ constexpr int kTripleXN = 17;        // first field of the unused-LED coordinate
 constexpr int kTripleFields = kTripleXN + 3 * (MPE_MAX_LEDS - 3);   // K2 LED-triple table fields (doubles)
 constexpr int kK2Queue = 192;        // hypotheses a K2 CTA can park for exact scoring before it scores in place
 constexpr int kK2Survivors = 768;    // problems a K2 CTA can park between tier 1 and the exact solve
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: what has been requested is remembered per device
+// (one static cache per kernel instantiation), so that a context on a second device of the same process gets its own call.
+constexpr int kMaxDevices = 64;
+struct SmemAttrCache { std::atomic<size_t> bytes[kMaxDevices]; };
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemAttrCache& cache, size_t default_limit = 48 * 1024) {
+  if (bytes <= default_limit) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && bytes <= cache.bytes[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  if (tracked) {
+    size_t cur = cache.bytes[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !cache.bytes[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+  }
+  return cudaSuccess;
+}
 
 // Camera model as the kernels consume it.
 struct DevCamera {

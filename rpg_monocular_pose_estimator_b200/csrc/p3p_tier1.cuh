@@ -32,6 +32,28 @@
 // and by measurement.  mpe_set_k2_filter(ctx, 0) switches every filter off (all-exact arm).
 //
 // Host + device: the header also compiles with g++ (tests build it into oracle/libtier1_check.so).
+// ---------------------------------------------------------------------------------------------------------------------------
+// The P3P parametrisation and the quartic coefficient expressions restated in this file follow Laurent Kneip's algorithm as
+// distributed with the reference (monocular_pose_estimator_lib/src/p3p.cpp), whose licence requires this notice to be retained:
+//
+//   Copyright (c) 2011, Laurent Kneip, ETH Zurich.  All rights reserved.
+//
+//   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the following
+//   conditions are met:
+//     * Redistributions of source code must retain the above copyright notice, this list of conditions and the following
+//       disclaimer.
+//     * Redistributions in binary form must reproduce the above copyright notice, this list of conditions and the following
+//       disclaimer in the documentation and/or other materials provided with the distribution.
+//     * Neither the name of ETH Zurich nor the names of its contributors may be used to endorse or promote products derived
+//       from this software without specific prior written permission.
+//
+//   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED WARRANTIES, INCLUDING,
+//   BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE DISCLAIMED.  IN NO
+//   EVENT SHALL ETH ZURICH BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES
+//   (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS
+//   INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING
+//   NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
+// ---------------------------------------------------------------------------------------------------------------------------
 #pragma once
 #include <math.h>
 #include <stdint.h>

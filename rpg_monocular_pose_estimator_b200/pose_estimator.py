@@ -202,6 +202,15 @@ class Context:
     def copy_poses_device(self, dst_device_ptr: int, n: int):
         self.check(self.L.mpe_copy_poses_device(self.h, n, C.c_void_p(dst_device_ptr)))
 
+    def copy_results_device(self, dst_device_ptr: int, n: int):
+        self.check(self.L.mpe_copy_results_device(self.h, n, C.c_void_p(dst_device_ptr)))
+
+    def probe_fp64_peak(self) -> float:
+        """Measured FP64 throughput of the device in TFLOP/s (FMA = 2 flops)."""
+        v = C.c_double(0)
+        self.check(self.L.mpe_probe_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
     def synchronize(self):
         self.check(self.L.mpe_synchronize(self.h))
 
@@ -331,63 +340,50 @@ class PoseEstimator:
     def setPredictedTime(self, t): self.predicted_time_ = t
     def getPredictedTime(self): return self.predicted_time_
 
-    # ---- small host math (sequential, a few hundred flops per frame) ------------------------------
+    # ---- small host math (sequential, a few hundred flops per frame): ONE implementation, in the library -------------
+    # (csrc/tracking_math.cuh: the functions K4 runs per stream on the GPU, exported for the host as mpe_host_*)
     def project2d(self, point, transform):
         """pose_estimator.cpp:251-268"""
-        K = np.asarray(self.camera_matrix_K_, np.float64)
-        cam = np.zeros((3, 4)); cam[:, :3] = K
-        t = (cam @ np.asarray(transform, np.float64)) @ np.asarray(point, np.float64)
-        return t[:2] / t[2]
+        K = np.ascontiguousarray(self.camera_matrix_K_, np.float64)
+        T = np.ascontiguousarray(transform, np.float64)
+        p = np.ascontiguousarray(np.asarray(point, np.float64)[:3])
+        out = np.zeros(2)
+        self.ctx.check(self.ctx.L.mpe_host_project_markers(_dp(K), _dp(T), _dp(p), 1, _dp(out)))
+        return out
 
     def predictMarkerPositionsInImage(self):
         """pose_estimator.cpp:270-276"""
-        self.predicted_pixel_positions_ = np.array([self.project2d(p, self.predicted_pose_) for p in self.object_points_])
+        K = np.ascontiguousarray(self.camera_matrix_K_, np.float64)
+        T = np.ascontiguousarray(self.predicted_pose_, np.float64)
+        m = np.ascontiguousarray(np.asarray(self.object_points_, np.float64)[:, :3])
+        out = np.zeros((len(m), 2))
+        self.ctx.check(self.ctx.L.mpe_host_project_markers(_dp(K), _dp(T), _dp(m), len(m), _dp(out)))
+        self.predicted_pixel_positions_ = out
 
     @staticmethod
-    def _skew(w):
-        return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], np.float64)
-
-    @classmethod
-    def exponentialMap(cls, twist):
+    def exponentialMap(twist):
         """pose_estimator.cpp:962-994"""
-        ups, om = np.asarray(twist[:3], np.float64), np.asarray(twist[3:], np.float64)
-        th = float(np.linalg.norm(om)); th2 = th * th
-        O = cls._skew(om); O2 = O @ O
-        if th == 0:
-            R, V = np.eye(3), np.eye(3)
-        else:
-            R = np.eye(3) + O / th * math.sin(th) + O2 / th2 * (1 - math.cos(th))
-            V = np.eye(3) + (1 - math.cos(th)) / th2 * O + (th - math.sin(th)) / (th2 * th) * O2
-        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = V @ ups
-        return T
+        from . import _lib
+        t = np.ascontiguousarray(twist, np.float64); out = np.zeros((4, 4))
+        _lib.load_library().mpe_host_exponential_map(_dp(t), _dp(out))
+        return out
 
-    @classmethod
-    def logarithmMap(cls, trans):
+    @staticmethod
+    def logarithmMap(trans):
         """pose_estimator.cpp:996-1064 (same special cases)"""
-        R, t = np.asarray(trans)[:3, :3], np.asarray(trans)[:3, 3]
-        w_hat = np.zeros((3, 3))
-        if not (np.sum((R - np.eye(3)) ** 2) <= 1e-20 * min(np.sum(R ** 2), 3.0)):
-            temp = (np.trace(R) - 1) / 2
-            temp = 1.0 if temp > 1 else (-1.0 if temp < -1 else temp)
-            phi = math.acos(temp)
-            if phi != 0:
-                w_hat = (R - R.T) / (2 * math.sin(phi)) * phi
-        w = np.array([w_hat[2, 1], w_hat[0, 2], w_hat[1, 0]])
-        wn = float(np.linalg.norm(w))
-        if np.all(t == 0):
-            A_inv = np.zeros((3, 3))
-        elif wn == 0 or math.sin(wn) == 0:
-            A_inv = np.eye(3)
-        else:
-            A_inv = np.eye(3) - w_hat / 2 + (2 * math.sin(wn) - wn * (1 + math.cos(wn))) / (2 * wn * wn * math.sin(wn)) * (w_hat @ w_hat)
-        return np.concatenate([A_inv @ t, w])
+        from . import _lib
+        T = np.ascontiguousarray(trans, np.float64); out = np.zeros(6)
+        _lib.load_library().mpe_host_logarithm_map(_dp(T), _dp(out))
+        return out
 
     def predictPose(self, time_to_predict):
         """pose_estimator.cpp:232-244"""
         self.predicted_time_ = time_to_predict
-        delta = self.logarithmMap(np.linalg.inv(self.previous_pose_) @ self.current_pose_)
-        delta_hat = delta / (self.current_time_ - self.previous_time_) * (self.predicted_time_ - self.current_time_)
-        self.predicted_pose_ = self.current_pose_ @ self.exponentialMap(delta_hat)
+        out = np.zeros((4, 4))
+        self.ctx.check(self.ctx.L.mpe_host_predict_pose(_dp(np.ascontiguousarray(self.previous_pose_, np.float64)),
+                                                        _dp(np.ascontiguousarray(self.current_pose_, np.float64)),
+                                                        float(self.previous_time_), float(self.current_time_), float(time_to_predict), _dp(out)))
+        self.predicted_pose_ = out
 
     def findCorrespondences(self):
         """pose_estimator.cpp:372-392 with calculateMinDistancesAndPairs :862-906"""
@@ -401,11 +397,29 @@ class PoseEstimator:
             if math.sqrt(best) <= self.nearest_neighbour_pixel_tolerance_:
                 corr.append((i + 1, bj))
         self.correspondences_ = np.array(corr, np.uint32).reshape(-1, 2)
+        if len(self.image_points_) > MPE_MAX_DET:
+            self._compact_to_matched_detections()
+
+    def _compact_to_matched_detections(self):
+        """Capacity path, same as the device loop (csrc/k4_tracking.cu): the brute-force tables hold MPE_MAX_DET detections, so with
+        more than that the detections that are some LED's nearest neighbour are compacted to the front (ascending) and the
+        correspondence rows renumbered; checkCorrespondences / optimisePose continue on that list.  last_flags gets MPE_F_TOO_MANY_DET."""
+        used = sorted({int(c[1]) - 1 for c in self.correspondences_})
+        remap = {j: m + 1 for m, j in enumerate(used)}
+        self.image_points_ = np.asarray(self.image_points_, np.float64).reshape(-1, 2)[used].copy()
+        if len(self.distorted_detection_centers_) > max(used, default=-1):
+            self.distorted_detection_centers_ = np.asarray(self.distorted_detection_centers_)[used].copy()
+        self.correspondences_ = np.array([(c[0], remap[int(c[1]) - 1]) for c in self.correspondences_], np.uint32).reshape(-1, 2)
+        self.last_flags = getattr(self, "last_flags", 0) | 4          # MPE_F_TOO_MANY_DET
 
     # ---- device stages ----------------------------------------------------------------------------
     def initialise(self):
-        """pose_estimator.cpp:544-721 (K2 sweep + decode, K3 check) -> 0/1"""
+        """pose_estimator.cpp:544-721 (K2 sweep + decode, K3 check) -> 0/1.  More than MPE_MAX_DET (16) detections: the sweep's
+        tables do not hold them — no exception, 0 is returned with MPE_F_TOO_MANY_DET in last_flags (limits)."""
         self._push()
+        if len(self.image_points_) > MPE_MAX_DET:
+            self.last_flags = getattr(self, "last_flags", 0) | 4
+            return 0
         ok, hist, corr, pose = self.ctx.initialise(self.image_points_)
         self.last_histogram = hist
         self.correspondences_ = corr
@@ -418,6 +432,10 @@ class PoseEstimator:
         self._push()
         if len(self.correspondences_) < 4:
             return 0
+        if len(self.image_points_) > MPE_MAX_DET:
+            self._compact_to_matched_detections()
+            if len(self.image_points_) < 4:
+                return 0
         ok, pose = self.ctx.check_correspondences(self.image_points_, self.correspondences_)
         if ok:
             self.predicted_pose_ = pose

@@ -16,10 +16,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("mode", ["device_loop", "stage"])
-def test_cpp_shim_tracking_sequence(tmp_path, mode):
-    exe = os.path.join(ROOT, "build", "shim_demo")
+@pytest.mark.parametrize("types", ["standin", "real_types"])
+def test_cpp_shim_tracking_sequence(tmp_path, mode, types):
+    """types = real_types: the shim compiled with the reference's own type names (Eigen::Matrix..., cv::Mat; against the Eigen /
+    OpenCV stand-ins of oracle/) and driven by a copy of MPENode's call sequence incl. augmentImage."""
+    exe = os.path.join(ROOT, "build", "shim_demo" if types == "standin" else "shim_real_types_demo")
     if not os.path.exists(exe):
-        subprocess.check_call(["python", "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
+        subprocess.check_call(["python", "-c", "import __graft_entry__ as g; g.build_shim_demos()"], cwd=ROOT)
     sc = synth.make_stream_scene(20, n_leds=5, seed=21)
     p = sc.params
     scene = tmp_path / "scene.bin"

@@ -155,3 +155,29 @@ def test_error_codes(gpu_ctx_752):
     with pytest.raises(mpe.MpeError):
         gpu_ctx_752.set_camera(K, np.zeros(3))             # 3 distortion coefficients is not a model OpenCV accepts either
     gpu_ctx_752.set_camera(K, D)
+
+
+@pytest.mark.parametrize("n_coeffs", [0, 4, 5, 8, 12])
+def test_distortion_models_with_4_5_8_12_coefficients(gpu_ctx_752, n_coeffs):
+    """cv::undistortPoints (led_detector.cpp:97-98) takes 4, 5, 8 or 12 distortion coefficients (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]);
+    the undistort epilogue of K1b must match it to the last float bit for each of them — rational model and thin-prism terms included —
+    on LED frames (all detections kept) and on random blobs spread over the whole image."""
+    rng = np.random.default_rng(300 + n_coeffs)
+    K, D5 = synth.camera()
+    full = np.concatenate([D5, [0.013, -0.021, 0.0042], [0.0011, -0.0007, 0.0009, 0.0004]])     # k4 k5 k6, s1..s4: small but visible (~0.1-1 px)
+    D = full[:n_coeffs].copy()
+    sc = synth.make_cold_scene(4, n_leds=5, seed=77)
+    for f in range(4):
+        assert _compare(gpu_ctx_752, sc.frames[f], (0, 0, 752, 480), sc.params, K, D, f"D{n_coeffs} frame {f}") == 5
+    p = synth.Params(min_blob_area=1.0, max_blob_area=2000, max_width_height_distortion=0.95, max_circular_distortion=0.99)
+    total = 0
+    for it in range(12):
+        img = random_blob_image(rng, 480, 752, n_blobs=25, kind="ellipse")
+        total += _compare(gpu_ctx_752, img, (0, 0, 752, 480), p, K, D, f"D{n_coeffs} blobs {it}")
+    assert total > 60
+    if n_coeffs in (8, 12):          # the extra terms really move the points (the test would be vacuous otherwise)
+        ctx = gpu_ctx_752
+        ctx.set_camera(K, D); ctx.set_params(sc.params)
+        a, _, _ = ctx.find_leds(sc.frames[0], (0, 0, 752, 480))
+        ctx.set_camera(K, full[:5]); b, _, _ = ctx.find_leds(sc.frames[0], (0, 0, 752, 480))
+        assert np.abs(a - b).max() > 1e-3

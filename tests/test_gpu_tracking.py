@@ -251,3 +251,57 @@ def test_device_loop_matches_golden_tracking_fixture(gpu_ctx_752):
             assert r["gn_iters"] == g["iters"][f], f
             dt, dr = pose_error(r["pose"].reshape(4, 4), g["pose"][f])
             assert dt < 1e-6 and dr < 1e-6, (f, dt, dr)
+
+
+def test_more_than_16_detections_in_the_roi_keep_tracking(gpu_ctx_752):
+    """Capacity divergence made explicit.  The reference accepts any number of detections; the tables of the brute-force sweep hold
+    MPE_MAX_DET = 16.  In TRACKING mode that does not stop the pose path: the nearest neighbours are searched among all (up to 64)
+    detections as the reference does, the matched ones are compacted (MPE_F_TOO_MANY_DET is set, correspondence rows refer to the
+    compacted list) and checkCorrespondences / optimisePose continue — the pose must be the oracle's, which sees all detections.
+    In COLD mode (initialise() with more than 16 detections) the frame is flagged and left without a pose, no error."""
+    import torch
+    T = 14
+    sc = synth.make_stream_scene(T, n_leds=5, seed=4242)
+    frames = sc.frames.copy()
+    rng = np.random.default_rng(8)
+    cluttered = range(6, 11)
+    for t in cluttered:                                   # 14 extra spots inside the predicted ROI, >= 12 px away from every LED
+        led, _, _ = synth.project_distorted(sc.K, sc.D, sc.poses[t], sc.markers)
+        x0, y0 = led.min(0) - 15; x1, y1 = led.max(0) + 15
+        spots = []
+        while len(spots) < 14:
+            p = np.array([rng.uniform(x0, x1), rng.uniform(y0, y1)])
+            if min(np.linalg.norm(led - p, axis=1).min(), min([np.linalg.norm(q - p) for q in spots], default=99)) >= 12:
+                spots.append(p)
+        img = frames[t].astype(np.float64)
+        yy, xx = np.mgrid[0:sc.height, 0:sc.width]
+        for p in spots:
+            img += 400.0 * np.exp(-((xx - p[0]) ** 2 + (yy - p[1]) ** 2) / (2 * 2.0 ** 2))
+        frames[t] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    ctx = gpu_ctx_752
+    ctx.set_camera(sc.K, sc.D); ctx.set_params(sc.params); ctx.set_markers(sc.markers)
+    ctx.streams_reset(1)
+    ctx.streams_set_frame_map(0, 0)
+    dev = torch.from_numpy(frames).cuda()
+    est = pose_oracle.PoseEstimatorOracle(sc.K, sc.D, sc.markers, sc.params)
+    n_flagged = 0
+    for t in range(T):
+        r = results_to_arrays(ctx.streams_step_device(dev[t].data_ptr(), sc.width, sc.width * sc.height, sc.width, sc.height, [sc.times[t]]))[0]
+        upd = est.estimate_body_pose(frames[t], sc.times[t])
+        assert bool(r["updated"]) == upd and upd, t
+        dt, dr = pose_error(r["pose"].reshape(4, 4), est.predicted_pose())
+        assert dt < 1e-6 and dr < 1e-6 and r["gn_iters"] == est.gn_iterations(), (t, dt, dr)
+        if t in cluttered:
+            assert est.n_det > 16 and (r["flags"] & 4), (t, est.n_det, r["flags"])
+            n_flagged += 1
+            k = r["n_corr"]
+            corr, ocorr = r["corr"][:2 * k].reshape(k, 2), est.correspondences()
+            assert np.array_equal(corr[:, 0], ocorr[:, 0])                                   # same LEDs matched
+            odet = est.L.mpeo_get_image_vectors                                                 # (oracle keeps all detections)
+            assert r["n_det"] == len(set(ocorr[:, 1].tolist()))                              # compacted to the matched detections
+        else:
+            assert not (r["flags"] & 4)
+    assert n_flagged == len(cluttered)
+    # cold mode: a cluttered frame through the batch entry is flagged and has no pose
+    res = results_to_arrays(ctx.estimate_batch(frames[8:9]))[0]
+    assert res["updated"] == 0 and (res["flags"] & 4) and res["n_det"] > 16
