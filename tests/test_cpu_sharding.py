@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from rpg_monocular_pose_estimator_b200.sharding import shard_range, gather_poses
+from rpg_monocular_pose_estimator_b200.sharding import shard_range, gather_poses, gather_records, verify_gather
 
 
 def test_shard_range_partitions():
@@ -33,7 +33,13 @@ def _worker(rank, world, port, n_frames, q):
     # stand-in for the per-rank device result: pose f carries its global frame index
     local = torch.arange(a, b, dtype=torch.float64).reshape(-1, 1).repeat(1, 16)
     allp = gather_poses(local, world, dist)
-    q.put((rank, allp[:, 0].tolist()))
+    # the record gather of bench.py: equal blocks of raw result records, verified by checksum exchange
+    rec = (torch.arange(4 * 968, dtype=torch.int64) * (rank + 3) % 251).to(torch.uint8).reshape(4, 968)
+    table = gather_records(rec, world, dist)
+    ok = verify_gather(table, rec, rank, world, dist)
+    bad = table.clone(); bad[(1 - rank) * 4, 5] ^= 1                 # one flipped bit in the OTHER rank's block must be noticed
+    ok_bad = verify_gather(bad, rec, rank, world, dist)
+    q.put((rank, allp[:, 0].tolist(), table.shape[0], ok, ok_bad))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,7 +51,9 @@ def test_pose_gather_two_ranks_gloo():
     n_frames = 11                      # ragged: 6 + 5
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
     for p in procs: p.start()
-    res = dict(q.get(timeout=120) for _ in range(2))
+    got = [q.get(timeout=120) for _ in range(2)]
+    res = {g[0]: g[1] for g in got}
+    assert all(g[2] == 8 and g[3] is True and g[4] is False for g in got), got
     for p in procs: p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
     for r in range(2):

@@ -181,3 +181,23 @@ def test_distortion_models_with_4_5_8_12_coefficients(gpu_ctx_752, n_coeffs):
         a, _, _ = ctx.find_leds(sc.frames[0], (0, 0, 752, 480))
         ctx.set_camera(K, full[:5]); b, _, _ = ctx.find_leds(sc.frames[0], (0, 0, 752, 480))
         assert np.abs(a - b).max() > 1e-3
+
+
+def test_two_devices_in_one_process():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: a context on a second device of the same process must get
+    its own call (the scan kernel needs ~57 KB of dynamic shared memory at 752x480, above the 48 KB default).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import rpg_monocular_pose_estimator_b200 as mpe
+    sc = synth.make_cold_scene(2, n_leds=5, seed=11)
+    outs = []
+    for dev in (0, 1, 0):
+        ctx = mpe.Context(dev, 4, 752, 480)
+        outs.append(_compare(ctx, sc.frames[0], (0, 0, 752, 480), sc.params, sc.K, sc.D, f"device {dev}"))
+        ctx.set_markers(sc.markers)
+        from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+        res = results_to_arrays(ctx.estimate_batch(sc.frames))
+        assert res["updated"].sum() == 2
+        ctx.close()
+    assert outs == [5, 5, 5]
