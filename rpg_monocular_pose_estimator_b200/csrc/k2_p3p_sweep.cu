@@ -466,6 +466,8 @@ __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const
 #pragma unroll
     for (int i = 0; i < kNuDet; ++i) dreg[i] = sdet[(int)((dlist >> (4 * i)) & 15ull)];
   }
+  T1Problem Q;
+  t1_problem(f_1, f_2, b, p_1, p_2, d_12, Q);
   bool maybe = false;
 #if MPE_T1_UNROLL_K
 #pragma unroll
@@ -474,7 +476,7 @@ __device__ __forceinline__ bool tier1_maybe(const double* __restrict__ cb, const
 #endif
   for (int k = 0; k < 4; ++k) {
     T1Pose P;
-    const int st = t1_pose(R.rho[k], f_1, f_2, b, p_1, p_2, d_12, P);
+    const int st = t1_pose(R.rho[k], Q, P);
     if (st == 2) return true;
     if (st == 1) {
 #pragma unroll

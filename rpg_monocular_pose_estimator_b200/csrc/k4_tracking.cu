@@ -151,8 +151,12 @@ __global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n) return;
   StreamState& st = a.state[s];
-  const bool upd = a.a_gn[s] && a.updated[s];
-  if (upd) {
+  // short step: this stream needs a stage the short step does not contain (cold start, whole-image retry, re-initialisation) -> state
+  // untouched, the host repeats the step in full (track_begin recomputes the same prediction from the unchanged poses)
+  const bool needs_full = a.fast && (a.mode[s] == 0 || a.a_retry[s] || a.a_init[s]);
+  const bool upd = !needs_full && a.a_gn[s] && a.updated[s];
+  if (needs_full) {
+  } else if (upd) {
     for (int i = 0; i < 16; ++i) st.predicted_pose[i] = a.pose_io[(size_t)s * 16 + i];
     if (st.it_since_initialized < 2) st.it_since_initialized++;
     for (int i = 0; i < 16; ++i) { st.previous_pose[i] = st.current_pose[i]; st.current_pose[i] = st.predicted_pose[i]; }
@@ -166,7 +170,7 @@ __global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
   r.n_det = a.n_det[s];
   r.n_corr = a.n_corr[s];
   r.gn_iters = a.iters[s];
-  r.flags = a.flags[s] | a.track_flags[s] | (a.a_init[s] ? MPE_F_INITIALISED : 0);
+  r.flags = a.flags[s] | a.track_flags[s] | (a.a_init[s] ? MPE_F_INITIALISED : 0) | (needs_full ? kFlagNeedsFullStep : 0);
   r.init_ok = a.ok[s];
   const Roi roi = a.result_rois[s];
   r.roi.x = roi.x; r.roi.y = roi.y; r.roi.width = roi.w; r.roi.height = roi.h;

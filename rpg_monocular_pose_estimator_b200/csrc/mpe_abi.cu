@@ -103,15 +103,18 @@ struct mpe_ctx {
              fmap_total == o.fmap_total && fetch == o.fetch && cfg == o.cfg && st == o.st;
     }
   };
-  StepGraphKey graph_key{}, pending_key{};   // a key is run eagerly once (function attributes get configured), captured on its second use
-  bool have_pending = false;
-  cudaGraphExec_t graph_exec = nullptr;
+  // two cached graphs: [0] the complete step, [1] the short step (small n, every stream tracking; see run_streams_step)
+  StepGraphKey graph_key[2]{}, pending_key[2]{};   // a key is run eagerly once (function attributes get configured), captured on its second use
+  bool have_pending[2] = {false, false};
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  bool short_steps = true;                // MPE_SHORT_STEPS=0 disables the short tracking step
+  long long short_step_count = 0, short_step_fallbacks = 0;
   // image ingest of the host-image tracking step (mpe_streams_step)
   int ingest_mode = MPE_INGEST_AUTO;
   std::vector<uint8_t> stream_tracking;   // host mirror: stream s has produced a pose since the last reset (it_since_initialized_ >= 1)
   int n_tracking = 0;
   long long h2d_bytes_copied = 0, zero_copy_steps = 0, copy_steps = 0;
-  long long graph_launches = 0;           // kernel launches contained in one replay
+  long long graph_launches[2] = {0, 0};   // kernel launches contained in one replay
   long long graph_replays = 0;
 };
 
@@ -521,6 +524,7 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.combos, B * kMaxCombos * kComboFields));
   CREATE_TRY(dev_alloc(&c->d.triples, (size_t)kTripleFields * kMaxPerms));
   { const char* e = getenv("MPE_K2_NO_FILTER"); if (e && e[0] == '1') c->k2_filter = 0; }
+  { const char* e = getenv("MPE_SHORT_STEPS"); if (e && e[0] == '0') c->short_steps = false; }
   { const char* e = getenv("MPE_K2_FILTER"); if (e && e[0] >= '0' && e[0] <= '2') c->k2_filter = e[0] - '0'; }
   CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.n_corr, B));
@@ -580,7 +584,7 @@ void mpe_destroy(mpe_ctx* c) {
   if (c->h_results) cudaFreeHost(c->h_results);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
-  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  for (int gi = 0; gi < 2; ++gi) if (c->graph_exec[gi]) cudaGraphExecDestroy(c->graph_exec[gi]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -997,7 +1001,7 @@ int mpe_streams_set_frame_map(mpe_ctx* c, const int* frame_index_device, int n_f
 }
 
 // Enqueues one estimateBodyPose step (pose_estimator.cpp:62-147) for n streams on `st`; the time stamps are already in c->d.times.
-static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st) {
+static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st, bool fast) {
   const int width = src.width, height = src.height;
   const size_t B = (size_t)c->max_batch;
   TrackArgs t{};
@@ -1007,6 +1011,7 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   t.mode = c->d.masks; t.done = c->d.masks + B; t.a_retry = c->d.masks + 2 * B; t.a_check = c->d.masks + 3 * B;
   t.a_init = c->d.masks + 4 * B; t.a_gn = c->d.masks + 5 * B;
   t.track_flags = c->d.track_flags;
+  t.fast = fast ? 1 : 0;
   t.n_det = c->d.n_det; t.flags = c->d.flags; t.det = c->d.det; t.centers = c->d.centers;
   t.corr = c->d.corr; t.n_corr = c->d.n_corr; t.pose_io = c->d.pose; t.cov = c->d.cov; t.ok = c->d.ok; t.iters = c->d.iters; t.updated = c->d.updated;
   Roi full{0, 0, width, height};
@@ -1015,48 +1020,54 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, nullptr);   // findLeds(ROI)
   if (rc != MPE_OK) return rc;
   CUDA_TRY(c, launch_track_after_detect(t, 0, st));                                              // + empties the ROI of streams that do not retry
-  rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, t.a_retry);  // whole-image retry (only where needed)
-  if (rc != MPE_OK) return rc;
-  CUDA_TRY(c, launch_track_after_detect(t, 1, st));
+  if (!fast) {
+    rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, t.a_retry);  // whole-image retry (only where needed)
+    if (rc != MPE_OK) return rc;
+    CUDA_TRY(c, launch_track_after_detect(t, 1, st));
+    ++c->launches;
+  }
   rc = run_refine(c, 0, n, 1, st, t.a_check, t.a_gn, t.a_init);                                  // checkCorrespondences on the NN matches; ok -> GN, else -> initialise()
   if (rc != MPE_OK) return rc;
-  rc = run_sweep(c, 0, n, st, t.a_init);                                                         // initialise(): cold streams + failed checks
-  if (rc != MPE_OK) return rc;
-  rc = run_refine(c, 0, n, 1, st, t.a_init, t.a_gn, nullptr);                                    // its check; ok -> GN
-  if (rc != MPE_OK) return rc;
+  if (!fast) {
+    rc = run_sweep(c, 0, n, st, t.a_init);                                                       // initialise(): cold streams + failed checks
+    if (rc != MPE_OK) return rc;
+    rc = run_refine(c, 0, n, 1, st, t.a_init, t.a_gn, nullptr);                                  // its check; ok -> GN
+    if (rc != MPE_OK) return rc;
+  }
   rc = run_refine(c, 0, n, 2, st, t.a_gn);                                                       // optimisePose
   if (rc != MPE_OK) return rc;
   CUDA_TRY(c, launch_track_finish(t, c->d.results, st));
-  c->launches += 4;
+  c->launches += 3;
   return MPE_OK;
 }
 
 // The step as one CUDA-graph replay: captured once per (frame buffer, geometry, configuration) key, then a single
 // cudaGraphLaunch replaces ~30 kernel/memset launches — what makes a one-camera, one-image-at-a-time caller (the way MPENode
 // drives the reference, monocular_pose_estimator.cpp:133-159) latency-competitive.  Per-kernel event timing disables replay.
-static int run_streams_step(mpe_ctx* c, const FrameSource& src, int n, const double* times, bool fetch) {
+static int run_streams_step(mpe_ctx* c, const FrameSource& src, int n, const double* times, bool fetch, bool fast = false) {
+  const int gi = fast ? 1 : 0;
   cudaStream_t st = c->stream;
   CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
   if (!c->use_graphs || c->timing) {
-    int rc = enqueue_streams_step(c, src, n, st);
+    int rc = enqueue_streams_step(c, src, n, st, fast);
     if (rc != MPE_OK) return rc;
     if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
     return MPE_OK;
   }
   mpe_ctx::StepGraphKey key{src.base, src.pitch, src.frame_stride, src.width, src.height, n, c->frame_map, c->frame_map_total, fetch ? 1 : 0,
                             c->cfg_version, st};
-  if (!c->graph_exec || !(key == c->graph_key)) {
-    if (!c->have_pending || !(key == c->pending_key)) {      // first use of this key: plain launches
-      c->pending_key = key; c->have_pending = true;
-      int rc = enqueue_streams_step(c, src, n, st);
+  if (!c->graph_exec[gi] || !(key == c->graph_key[gi])) {
+    if (!c->have_pending[gi] || !(key == c->pending_key[gi])) {      // first use of this key: plain launches
+      c->pending_key[gi] = key; c->have_pending[gi] = true;
+      int rc = enqueue_streams_step(c, src, n, st, fast);
       if (rc != MPE_OK) return rc;
       if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
       return MPE_OK;
     }
-    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    if (c->graph_exec[gi]) { cudaGraphExecDestroy(c->graph_exec[gi]); c->graph_exec[gi] = nullptr; }
     const long long l0 = c->launches;
     CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_streams_step(c, src, n, st);
+    int rc = enqueue_streams_step(c, src, n, st, fast);
     cudaError_t ce = cudaSuccess;
     if (rc == MPE_OK && fetch) ce = cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st);
     cudaGraph_t g = nullptr;
@@ -1066,15 +1077,15 @@ static int run_streams_step(mpe_ctx* c, const FrameSource& src, int n, const dou
       if (g) cudaGraphDestroy(g);
       return fail(c, MPE_E_CUDA, std::string("stream capture of the tracking step failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
     }
-    cudaError_t ie = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaError_t ie = cudaGraphInstantiate(&c->graph_exec[gi], g, 0);
     cudaGraphDestroy(g);
-    if (ie != cudaSuccess) { c->graph_exec = nullptr; return fail(c, MPE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
-    c->graph_launches = c->launches - l0;
+    if (ie != cudaSuccess) { c->graph_exec[gi] = nullptr; return fail(c, MPE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    c->graph_launches[gi] = c->launches - l0;
     c->launches = l0;                        // nothing ran during the capture
-    c->graph_key = key;
+    c->graph_key[gi] = key;
   }
-  CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, st));
-  c->launches += c->graph_launches;
+  CUDA_TRY(c, cudaGraphLaunch(c->graph_exec[gi], st));
+  c->launches += c->graph_launches[gi];
   ++c->graph_replays;
   return MPE_OK;
 }
@@ -1088,6 +1099,29 @@ static int finish_step(mpe_ctx* c, int n, mpe_result* results) {
   for (int i = 0; i < n; ++i)
     if (results[i].updated && !c->stream_tracking[i]) { c->stream_tracking[i] = 1; ++c->n_tracking; }
   return MPE_OK;
+}
+
+// The short step serves the latency case: a handful of cameras, all of them tracking.  It leaves out the stages that a tracking
+// stream almost never needs (whole-image retry: 5 launches; brute-force re-initialisation and its check: 6 launches); a stream that
+// does need one is left untouched and flagged, and the complete step is run right after (the records are read on the host anyway).
+constexpr int kShortStepMaxStreams = 64;
+static bool want_short_step(const mpe_ctx* c, int n, bool fetch) {
+  return c->short_steps && fetch && n <= kShortStepMaxStreams && c->n_tracking >= n && !c->timing;
+}
+static bool short_step_incomplete(const mpe_ctx* c, int n) {
+  for (int i = 0; i < n; ++i) if (c->h_results[i].flags & mpe::kFlagNeedsFullStep) return true;
+  return false;
+}
+
+static int run_short_then_full(mpe_ctx* c, const FrameSource& src, int n, const double* times) {
+  const bool fast = want_short_step(c, n, true);
+  int rc = run_streams_step(c, src, n, times, true, fast);
+  if (rc != MPE_OK || !fast) return rc;
+  ++c->short_step_count;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (!short_step_incomplete(c, n)) return MPE_OK;
+  ++c->short_step_fallbacks;
+  return run_streams_step(c, src, n, times, true, false);
 }
 
 // Is `p` page-locked host memory the GPU can read in place (cudaHostAlloc / cudaHostRegister)?  Returns its device alias.
@@ -1109,8 +1143,18 @@ int mpe_streams_step_device(mpe_ctx* c, const uint8_t* frames_device, int pitch,
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int total = c->frame_map ? c->frame_map_total : n_streams;
   FrameSource src{frames_device, pitch, frame_stride, width, height, total};
-  rc = run_streams_step(c, src, n_streams, times, results != nullptr);
+  const bool fast = want_short_step(c, n_streams, results != nullptr);
+  rc = run_streams_step(c, src, n_streams, times, results != nullptr, fast);
   if (rc != MPE_OK) return rc;
+  if (fast) {
+    ++c->short_step_count;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (short_step_incomplete(c, n_streams)) {
+      ++c->short_step_fallbacks;
+      rc = run_streams_step(c, src, n_streams, times, true, false);
+      if (rc != MPE_OK) return rc;
+    }
+  }
   return finish_step(c, n_streams, results);
 }
 
@@ -1143,7 +1187,7 @@ int mpe_streams_step(mpe_ctx* c, const uint8_t* frames, int pitch, long long fra
   if (zero_copy) {
     ++c->zero_copy_steps;
     FrameSource src{alias, pitch, frame_stride, width, height, n_streams};
-    rc = run_streams_step(c, src, n_streams, times, true);
+    rc = run_short_then_full(c, src, n_streams, times);
   } else {
     ++c->copy_steps;
     c->h2d_bytes_copied += (long long)n_streams * width * height;
@@ -1157,7 +1201,7 @@ int mpe_streams_step(mpe_ctx* c, const uint8_t* frames, int pitch, long long fra
                                       cudaMemcpyHostToDevice, st));
     }
     FrameSource src{c->d.frames, c->pitch, dev_stride, width, height, n_streams};
-    rc = run_streams_step(c, src, n_streams, times, true);
+    rc = run_short_then_full(c, src, n_streams, times);
   }
   c->frame_map = saved_map; c->frame_map_total = saved_total;
   if (rc != MPE_OK) return rc;

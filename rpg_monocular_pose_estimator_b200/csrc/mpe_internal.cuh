@@ -67,6 +67,7 @@ struct DevPoseParams {
   double markers[3 * MPE_MAX_LEDS];
 };
 
+constexpr int kFlagNeedsFullStep = 1 << 30;   // internal record flag of the short tracking step, never returned to callers
 struct Roi { int x, y, w, h; };   // same layout as mpe_rect / cv::Rect
 
 // Geometry of one K1 launch (uniform over the batch unless `rois` is given).
@@ -189,6 +190,8 @@ struct TrackArgs {
   double* pred_px;           // [n][MPE_MAX_LEDS][2] predicted_pixel_positions_
   uint8_t *mode, *done, *a_retry, *a_check, *a_init, *a_gn;   // [n] each
   int* track_flags;          // [n]
+  int fast;                  // 1: the short step (no whole-image retry, no re-initialisation stages): a stream that would need them is
+                             //    left untouched and flagged kFlagNeedsFullStep, the host then runs the complete step
   // buffers shared with the cold path
   const int* n_det; const int* flags; const double* det; const float* centers;
   uint32_t* corr; int* n_corr; double* pose_io; const double* cov; int* ok; int* iters; int* updated;

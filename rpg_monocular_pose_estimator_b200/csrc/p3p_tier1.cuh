@@ -81,6 +81,32 @@ constexpr double kT1Cancel = MPE_T1_CANCEL;         // Q/2 over |R| in the refer
 constexpr double kT1SmallW = 1e-5;        // w^2 = z below this fraction of |alpha| + sqrt|gamma|: the reference divides 2 beta by a w that is mostly rounding -> maybe
 constexpr double kT1ResRel = 1e-9;        // factorisation residual |u v - c| relative to the terms -> maybe
 
+// Tier 1 needs ~1e-12 relative accuracy, not correct rounding: reciprocal and reciprocal square root from a float seed and
+// Newton steps in double — five to eight branch-free instructions instead of the ~25 (with slow-path branches) of an IEEE
+// double division / square root.  Arguments outside the float range give inf / NaN, which every caller turns into "maybe".
+MPE_HD double t1_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r = (double)__frcp_rn((float)x);
+#else
+  double r = (double)(1.0f / (float)x);
+#endif
+  r = T1_FMA(T1_FMA(-x, r, 1.0), r, r);          // r (2 - x r): 1e-7 -> 1e-14
+  r = T1_FMA(T1_FMA(-x, r, 1.0), r, r);          // -> rounding
+  return r;
+}
+MPE_HD double t1_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double y = (double)rsqrtf((float)x);
+#else
+  double y = (double)(1.0f / sqrtf((float)x));
+#endif
+  const double hx = 0.5 * x;
+  y = T1_FMA(T1_FMA(-hx * y, y, 0.5), y, y);      // y (1.5 - x y^2 / 2)
+  y = T1_FMA(T1_FMA(-hx * y, y, 0.5), y, y);
+  return y;
+}
+MPE_HD double t1_sqrt(double x) { return (x > 0.0) ? x * t1_rsqrt(x) : ((x == 0.0) ? 0.0 : x * t1_rsqrt(x)); }
+
 #ifdef MPE_T1_DEBUG
 struct T1Debug { double al, be, ga, z, kappa, d1, d2; };
 static T1Debug g_t1_debug;
@@ -98,15 +124,16 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
   const double F11 = f_1 * f_1, F22 = f_2 * f_2, F12 = f_1 * f_2;
   const double a = p_1, c = p_2, d = d_12;
   const double a2 = a * a, c2 = c * c, d2 = d * d, b2 = b * b, ad = a * d;
-  // factors[k] / c^2 (c = p_2 != 0 for a usable triple); same polynomials as p3p.cpp:171-185
+  // factors[k] / c^2 for k = 0, 1, 2, factors[3] / c and factors[4] as they are (c = p_2 != 0 for a usable triple): the same
+  // polynomials as p3p.cpp:171-185, normalised by the leading one with ONE reciprocal
   const double g0 = F22 + F11 + 1.0;
-  const double A = -(c2 * g0);
   const double B = 2.0 * c * d * (T1_FMA(b, 1.0 + F22, -F12));
   const double C = T1_FMA(-F22, a2 + d2 * b2 + d2 - c2 - 2.0 * ad, T1_FMA(c2 - a2, F11, T1_FMA(2.0 * ad, 1.0 + F12 * b, -(d2 * b2 + 2.0 * a2))));
-  const double Dq = 2.0 * d * (T1_FMA(a2 - ad, b, c2 * (F12 - F22 * b))) / c;
-  const double E = (T1_FMA(F22 * c2, d2 + a2 + d2 * b2 - 2.0 * ad, T1_FMA(-2.0 * F12 * c2, ad * b, T1_FMA(c2 * F11, a2, a2 * (2.0 * ad - d2 - a2))))) / c2;
-  const double iA = 1.0 / A;
-  const double Bn = B * iA, Cn = C * iA, Dn = Dq * iA, En = E * iA;
+  const double D3 = 2.0 * d * (T1_FMA(a2 - ad, b, c2 * (F12 - F22 * b)));
+  const double E4 = T1_FMA(F22 * c2, d2 + a2 + d2 * b2 - 2.0 * ad, T1_FMA(-2.0 * F12 * c2, ad * b, T1_FMA(c2 * F11, a2, a2 * (2.0 * ad - d2 - a2))));
+  const double ic = t1_rcp(c);
+  const double iA = -t1_rcp(g0) * ic * ic;            // 1 / (factors[0] / c^2)
+  const double Bn = B * iA, Cn = C * iA, Dn = D3 * ic * iA, En = E4 * (ic * ic) * iA;
   // depressed quartic t^4 + al t^2 + be t + ga, x = t + sh
   const double Bn2 = Bn * Bn;
   const double al = T1_FMA(-0.375, Bn2, Cn);
@@ -125,8 +152,8 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
   g_t1_debug.al = al; g_t1_debug.be = be; g_t1_debug.ga = ga; g_t1_debug.kappa = 0; g_t1_debug.z = 0; g_t1_debug.d1 = g_t1_debug.d2 = 0;
 #endif
   if (qz > 0.0 && disc > 0.0) {
-    const double sq = sqrt(disc);
-    const double Rq = ((1.0 / 27.0) * pz * pz * pz) / (sq + 0.5 * qz);       // = sqrt(disc) - qz/2 without the cancellation
+    const double sq = t1_sqrt(disc);
+    const double Rq = ((1.0 / 27.0) * pz * pz * pz) * t1_rcp(sq + 0.5 * qz);  // = sqrt(disc) - qz/2 without the cancellation
 #ifdef MPE_T1_DEBUG
     g_t1_debug.kappa = 0.5 * qz / fabs(Rq);
 #endif
@@ -137,10 +164,10 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
     const float sq = sqrtf((float)disc);
     const float hq = (float)(-0.5 * qz);
     const float big = (hq >= 0.f) ? cbrtf(hq + sq) : cbrtf(hq - sq);
-    wseed = big + ((big != 0.f) ? (float)(-pz / 3.0) / big : 0.f);
+    wseed = big + ((big != 0.f) ? (float)(pz * (-1.0 / 3.0)) / big : 0.f);
   } else {
-    const float m = 2.f * sqrtf((float)(-pz / 3.0));
-    float arg = (float)(3.0 * qz / pz) / m;
+    const float m = 2.f * sqrtf((float)(pz * (-1.0 / 3.0)));
+    float arg = 3.f * (float)qz / ((float)pz * m);
     arg = fminf(1.f, fmaxf(-1.f, arg));
     wseed = m * cosf(acosf(arg) * (1.f / 3.f));
   }
@@ -148,14 +175,15 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
   double corr = 0.0;
 #pragma unroll
   for (int it = 0; it < 3; ++it) {
-    const double g = T1_FMA(T1_FMA(T1_FMA(z, 1.0, c2z), z, c1z), z, c0z);
+    const double g = T1_FMA(T1_FMA(z + c2z, z, c1z), z, c0z);
     const double gp = T1_FMA(T1_FMA(3.0, z, 2.0 * c2z), z, c1z);
-    corr = g / gp;
+    corr = g * t1_rcp(gp);
     z -= corr;
   }
-  if (!(z > kT1SmallW * (fabs(al) + sqrt(fabs(ga)))) || !(fabs(corr) <= 1e-9 * z)) { R.maybe = 1; return; }   // also catches NaN, and be == 0 (biquadratic: z may be 0)
-  const double s = sqrt(z);
-  const double bs = be / s;
+  if (!(z > kT1SmallW * (fabs(al) + t1_sqrt(fabs(ga)))) || !(fabs(corr) <= 1e-9 * z)) { R.maybe = 1; return; }   // also catches NaN, and be == 0 (biquadratic: z may be 0)
+  const double is = t1_rsqrt(z);
+  const double s = z * is;
+  const double bs = be * is;
   const double u = 0.5 * (al + z - bs), v = 0.5 * (al + z + bs);
   if (!(fabs(T1_FMA(u, v, -ga)) <= kT1ResRel * (fabs(u * v) + fabs(ga) + z * z))) { R.maybe = 1; return; }
   const double d1 = T1_FMA(-4.0, u, z), d2q = T1_FMA(-4.0, v, z);
@@ -163,36 +191,55 @@ MPE_HD void t1_quartic_roots(double f_1, double f_2, double b, double p_1, doubl
   g_t1_debug.z = z; g_t1_debug.d1 = d1; g_t1_debug.d2 = d2q;
 #endif
   if (!(fabs(d1) > kT1PairSep * kT1PairSep) || !(fabs(d2q) > kT1PairSep * kT1PairSep)) { R.maybe = 1; return; }   // separation = sqrt(|disc|)
-  if (d1 >= 0.0) { const double r = sqrt(d1); R.rho[0] = 0.5 * (-s + r) + sh; R.rho[1] = 0.5 * (-s - r) + sh; }
+  if (d1 >= 0.0) { const double r = t1_sqrt(d1); R.rho[0] = 0.5 * (-s + r) + sh; R.rho[1] = 0.5 * (-s - r) + sh; }
   else { R.rho[0] = R.rho[1] = -0.5 * s + sh; }
-  if (d2q >= 0.0) { const double r = sqrt(d2q); R.rho[2] = 0.5 * (s + r) + sh; R.rho[3] = 0.5 * (s - r) + sh; }
+  if (d2q >= 0.0) { const double r = t1_sqrt(d2q); R.rho[2] = 0.5 * (s + r) + sh; R.rho[3] = 0.5 * (s - r) + sh; }
   else { R.rho[2] = R.rho[3] = 0.5 * s + sh; }
   R.n = 4;
 }
 
-// Root-dependent scalars of the back-substitution (p3p.cpp:196-220) without divisions by f_2.
+// Back-substitution (p3p.cpp:196-220) without divisions by f_2: cot(alpha) = num/den with both multiplied by f_2 (the sign of the
+// pair is irrelevant), num = cn0 - rho cn1, den = cd0 - rho cd1.  The four constants are per problem.
+struct T1Problem {
+  double cn0, cn1, cd0, cd1;
+  double h2_min;        // |(num, den)|^2 below this: cot(alpha) is 0/0-like -> maybe
+  double b, d_12;
+};
+MPE_HD void t1_problem(double f_1, double f_2, double b, double p_1, double p_2, double d_12, T1Problem& Q) {
+  Q.cn1 = p_2 * f_2;
+  Q.cn0 = T1_FMA(d_12 * b, f_2, -(f_1 * p_1));
+  Q.cd1 = f_1 * p_2;
+  Q.cd0 = (p_1 - d_12) * f_2;
+  const double scale = fabs(f_2) * (fabs(p_1) + fabs(p_2) + d_12 * (1.0 + fabs(b))) + fabs(f_1) * (fabs(p_1) + fabs(p_2));
+  Q.h2_min = 1e-16 * scale * scale;
+  Q.b = b; Q.d_12 = d_12;
+}
+// Root-dependent scalars
 struct T1Pose {
   double rho, st;       // cos(theta), sin(theta)
   double sa, ca;        // sin(alpha), cos(alpha)
   double dk;            // d_12 * (sin(alpha) b + cos(alpha))
 };
 // returns 0: the reference's hypothesis is NaN (no vote), 1: usable, 2: maybe (ill-conditioned)
-MPE_HD int t1_pose(double rho, double f_1, double f_2, double b, double p_1, double p_2, double d_12, T1Pose& P) {
+MPE_HD int t1_pose(double rho, const T1Problem& Q, T1Pose& P) {
   const double om = T1_FMA(-rho, rho, 1.0);
   if (om < -kT1RootMargin2) return 0;
   if (!(om >= kT1NearOne)) return 2;
-  // cot(alpha) = num/den, both multiplied by f_2 (the sign of the pair is irrelevant)
-  const double num = T1_FMA(-rho, p_2 * f_2, T1_FMA(d_12 * b, f_2, -(f_1 * p_1)));
-  const double den = T1_FMA(-rho, f_1 * p_2, (p_1 - d_12) * f_2);
+  const double num = T1_FMA(-rho, Q.cn1, Q.cn0);
+  const double den = T1_FMA(-rho, Q.cd1, Q.cd0);
   const double h2 = T1_FMA(num, num, den * den);
-  const double scale = fabs(f_2) * (fabs(p_1) + fabs(p_2) + d_12 * (1.0 + fabs(b))) + fabs(f_1) * (fabs(p_1) + fabs(p_2));
-  if (!(h2 > 1e-16 * scale * scale)) return 2;
-  const double ih = 1.0 / sqrt(h2);
-  P.rho = rho; P.st = sqrt(om);
+  if (!(h2 > Q.h2_min)) return 2;
+  const double ih = t1_rsqrt(h2);
+  P.rho = rho; P.st = om * t1_rsqrt(om);
   P.sa = fabs(den) * ih;
   P.ca = ((den >= 0.0) ? num : -num) * ih;
-  P.dk = d_12 * T1_FMA(P.sa, b, P.ca);
+  P.dk = Q.d_12 * T1_FMA(P.sa, Q.b, P.ca);
   return 1;
+}
+MPE_HD int t1_pose(double rho, double f_1, double f_2, double b, double p_1, double p_2, double d_12, T1Pose& P) {
+  T1Problem Q;
+  t1_problem(f_1, f_2, b, p_1, p_2, d_12, Q);
+  return t1_pose(rho, Q, P);
 }
 
 // K x_c (homogeneous pixel coordinates, not normalised) of an LED given in the triple's frame N; Mc = K [e1 e2 e3] (columns).

@@ -126,7 +126,7 @@ def test_host_step_single_camera_graph_replay_matches_oracle(gpu_ctx_752):
                 assert dt < 1e-6 and dr < 1e-6, (tag, dt, dr)
                 assert r["gn_iters"] == est.gn_iterations(), tag
         assert n_upd >= T - 4
-        assert ctx.launch_count() - l0 >= 18 * T      # every step, replayed or not, accounts for its 18 kernel launches
+        assert ctx.launch_count() - l0 >= 9 * T       # every step, replayed or not, accounts for its kernel launches (short step: 10, complete step: 21)
 
 
 def test_host_step_equals_device_step_and_follows_reconfiguration(gpu_ctx_752):
