@@ -45,6 +45,9 @@ struct t1c_stats {
 };
 
 // One frame: K row-major, markers n_obj x 3, det n_det x 2 (undistorted pixels), tolerance and margin in pixels.
+static int g_fp32 = 1;
+extern "C" void t1c_set_fp32(int on) { g_fp32 = on; }
+
 void t1c_frame(const double K[9], const double* mk, int n_obj, const double* det, int n_det, double tol, double margin, t1c_stats* S) {
   const double r = tol + margin;
   const double tol_sq = tol * tol;
@@ -121,6 +124,20 @@ void t1c_frame(const double K[9], const double* mk, int n_obj, const double* det
               const int ll = nth_unused(m, oa, ob, oc);
               const v3 dx = v_sub(P(ll), W.P1);
               double au, av, az, l1;
+              if (g_fp32) {
+                float Mcf[9]; for (int e = 0; e < 9; ++e) Mcf[e] = (float)Mc[e];
+                float fu, fv, fz, fl;
+                t1_project_f(t1_pose_f(Pk[k]), Mcf, (float)v_dot(W.n1, dx), (float)v_dot(W.n2, dx), (float)v_dot(W.n3, dx), fu, fv, fz, fl);
+                t1px[k][m][0] = fu; t1px[k][m][1] = fv; t1px[k][m][2] = fz;
+                if (!(std::fabs(fz) >= 1e-3f * fl) || !(fl >= 1e-3f * (float)W.d_12)) maybe = true;
+                const float rf = (float)r, lim = rf * rf * (fz * fz);
+                for (int i = 0; i < nu_det; ++i) {
+                  const int kk = nth_unused(i, d0, d1, d2);
+                  const float eu = fu - (float)det[2 * kk] * fz, ev = fv - (float)det[2 * kk + 1] * fz;
+                  if (!(eu * eu + ev * ev > lim)) maybe = true;
+                }
+                continue;
+              }
               t1_project(Pk[k], Mc, v_dot(W.n1, dx), v_dot(W.n2, dx), v_dot(W.n3, dx), au, av, az, l1);
               t1px[k][m][0] = au; t1px[k][m][1] = av; t1px[k][m][2] = az;
               if (!(std::fabs(az) >= 1e-3 * l1) || !(l1 >= 1e-3 * W.d_12)) maybe = true;

@@ -65,8 +65,10 @@
 #endif
 #if defined(__CUDA_ARCH__)
 #define T1_FMA(a, b, c) fma((a), (b), (c))
+#define T1_FMAF(a, b, c) fmaf((a), (b), (c))
 #else
 #define T1_FMA(a, b, c) ((a) * (b) + (c))
+#define T1_FMAF(a, b, c) ((a) * (b) + (c))
 #endif
 
 namespace mpe {
@@ -253,6 +255,29 @@ MPE_HD void t1_project(const T1Pose& P, const double Mc[9], double X0, double X1
   av = T1_FMA(Mc[3], v0, T1_FMA(Mc[4], v1, Mc[5] * v2));
   az = T1_FMA(Mc[6], v0, T1_FMA(Mc[7], v1, Mc[8] * v2));
   l1 = fabs(v0) + fabs(v1) + fabs(v2);          // |x_c|_1 up to the rotation T (within sqrt(3))
+}
+
+
+// The same projection in FP32 (compile-time option MPE_T1_FP32=1; the default build keeps double): roots and the root-dependent scalars stay in double, the unused LED's
+// homogeneous pixel coordinates and the comparisons against the unused detections are single precision.  Error budget against the
+// 0.25 px margin: |v| ~ 1 m and |Mc| <= ~1e3 give |a| ~ 1e3 with a rounding error of a few 1e-4, i.e. < 1e-3 px after the
+// (implicit) division by a_z >= 1e-3 |v|_1 ... in practice a_z ~ |v|; the products u a_z add 752 * 6e-8.  Measured by
+// tests/test_cpu_k2_tier1.py (host build, same float arithmetic): the deviation from the exact back-projection stays below
+// 3e-3 px on unflagged problems.  Halves the registers tier 1 holds (K T^T, the LED coordinates, the detections) and moves
+// 60 % of its arithmetic to the otherwise idle FP32 pipe.
+struct T1PoseF { float rho, st, sa, ca, dk; };
+MPE_HD T1PoseF t1_pose_f(const T1Pose& P) {
+  T1PoseF F; F.rho = (float)P.rho; F.st = (float)P.st; F.sa = (float)P.sa; F.ca = (float)P.ca; F.dk = (float)P.dk; return F;
+}
+MPE_HD void t1_project_f(const T1PoseF& P, const float Mc[9], float X0, float X1, float X2, float& au, float& av, float& az, float& l1) {
+  const float g = T1_FMAF(P.rho, X1, P.st * X2);
+  const float v0 = T1_FMAF(-P.ca, X0, T1_FMAF(-P.sa, g, P.dk));
+  const float v1 = T1_FMAF(P.sa, X0, -(P.ca * g));
+  const float v2 = T1_FMAF(-P.st, X1, P.rho * X2);
+  au = T1_FMAF(Mc[0], v0, T1_FMAF(Mc[1], v1, Mc[2] * v2));
+  av = T1_FMAF(Mc[3], v0, T1_FMAF(Mc[4], v1, Mc[5] * v2));
+  az = T1_FMAF(Mc[6], v0, T1_FMAF(Mc[7], v1, Mc[8] * v2));
+  l1 = fabsf(v0) + fabsf(v1) + fabsf(v2);
 }
 
 }  // namespace mpe
