@@ -11,9 +11,14 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr = rows[1]
+    # a report holds one section per profiled kernel: "Kernel Name",<name> / header row / one row per SASS instruction
+    want = kern.replace("ILb0", "").replace("ILb1", "")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = next(i for i in starts if want.split("kernel")[0] in rows[i][1].replace("::", ""))
+    end = next((j for j in starts if j > sec), len(rows))
+    hdr = rows[sec + 1]
     ci = {n: i for i, n in enumerate(hdr)}
-    insts = [(r[ci["Source"]].strip(), float(r[ci["Instructions Executed"]] or 0), float(r[ci["# Samples"]] or 0)) for r in rows[2:] if len(r) > 5]
+    insts = [(r[ci["Source"]].strip(), float(r[ci["Instructions Executed"]] or 0), float(r[ci["# Samples"]] or 0)) for r in rows[sec + 2:end] if len(r) > 5]
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
     lines = None
