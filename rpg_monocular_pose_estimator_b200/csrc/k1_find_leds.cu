@@ -142,6 +142,7 @@ __device__ __forceinline__ TileCoord decode_listed(const K1Geom& g, uint32_t e, 
 
 // One thread per frame appends the tiles its ROI touches to the work list (order irrelevant: every tile is independent).
 __global__ void build_tile_list_kernel(const K1Geom g, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+  pdl_enter();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= g.n_frames) return;
   const Roi r = g.rois[f];
@@ -154,8 +155,7 @@ __global__ void build_tile_list_kernel(const K1Geom g, uint32_t* __restrict__ li
 }
 
 cudaError_t launch_build_tile_list(const K1Geom& g, uint32_t* list, uint32_t* count, cudaStream_t st) {
-  build_tile_list_kernel<<<(g.n_frames + 127) / 128, 128, 0, st>>>(g, list, count);
-  return cudaGetLastError();
+  return launch_k(build_tile_list_kernel, (g.n_frames + 127) / 128, 128, 0, st, g, list, count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,6 +176,7 @@ __host__ __device__ inline size_t k1_ring_offset() {
 
 template <bool kLowThr, int kStages>
 __global__ void __launch_bounds__(kK1Threads, 2) scan_kernel(const __grid_constant__ CUtensorMap tmap, const K1aArgs a) {
+  pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const K1Geom& g = a.g;
   const int R = a.radius;
@@ -325,6 +326,7 @@ __device__ __forceinline__ int blur_smem_words(int box_w, int tw_px) {
 
 template <int RT>   // RT > 0: radius known at compile time (fully unrolled); RT == 0: a.radius, generic loops (R up to kMaxRadius)
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const K1aArgs a) {
+  pdl_enter();
   const int R = (RT > 0) ? RT : a.radius;
   constexpr int kR = (RT > 0) ? RT : kMaxRadius;     // array bounds
   const int dj_max = (R + 3) >> 2;                    // source words that can influence an output word: j-dj_max .. j+dj_max
@@ -493,8 +495,7 @@ static cudaError_t launch_scan_inst(const K1aArgs& a, const CUtensorMap& tmap, i
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   int grid = n_tiles < n_sms * ctas_per_sm ? n_tiles : n_sms * ctas_per_sm;
   if (grid < 1) grid = 1;
-  kern<<<grid, kK1Threads, smem, st>>>(tmap, a);
-  return cudaGetLastError();
+  return launch_k(kern, grid, kK1Threads, smem, st, tmap, a);
 }
 
 static cudaError_t launch_scan(const K1aArgs& a, const CUtensorMap& tmap, int n_sms, cudaStream_t st) {
@@ -527,8 +528,7 @@ static cudaError_t launch_blur_r(const K1aArgs& a, int n_sms, cudaStream_t st) {
   if ((size_t)per_sm * (bsmem + 1024) > 220 * 1024) per_sm = (int)((220 * 1024) / (bsmem + 1024));
   if (per_sm < 1) per_sm = 1;
   int grid = n_tiles < n_sms * per_sm ? n_tiles : n_sms * per_sm;
-  blur_kernel<RT><<<grid, kBlurThreads, bsmem, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(blur_kernel<RT>, grid, kBlurThreads, bsmem, st, a);
 }
 
 cudaError_t launch_blur_tiles(const K1aArgs& a, int radius, int n_sms, cudaStream_t st) {
@@ -558,18 +558,25 @@ struct MaskView {
   int win_wpr;
 };
 
+// kWin: the launch holds the ROI's mask rows in shared memory (m.win valid for every frame-warp that takes this path)
+template <bool kWin>
 __device__ __forceinline__ uint32_t mv_word(const MaskView& m, int y, int wi) {
   // word wi of ROI row y, 0 where the producing tile reported no foreground in that row
+  if (kWin) {
+    if ((unsigned)y >= (unsigned)m.h || (unsigned)wi >= (unsigned)m.win_wpr) return 0u;
+    return m.win[y * m.win_wpr + wi];
+  }
   if ((unsigned)y >= (unsigned)m.h || wi < 0 || wi >= m.wpr) return 0u;
-  if (m.win) return (wi < m.win_wpr) ? m.win[y * m.win_wpr + wi] : 0u;
   int ct = (m.roi_n_ct == 1) ? 0 : min(wi / m.words_per_ct, m.roi_n_ct - 1);
   uint32_t fl = m.flags[(y >> 5) * m.n_ct + ct];
   if (!((fl >> (y & 31)) & 1u)) return 0u;
   return __ldg(m.mask + (size_t)y * m.wpr + wi);
 }
+template <bool kWin>
 __device__ __forceinline__ bool mv_bit(const MaskView& m, int x, int y) {
   if ((unsigned)x >= (unsigned)m.w || (unsigned)y >= (unsigned)m.h) return false;
-  return (mv_word(m, y, x >> 5) >> (x & 31)) & 1u;
+  if (kWin) return (m.win[y * m.win_wpr + (x >> 5)] >> (x & 31)) & 1u;      // x < w implies x >> 5 < win_wpr
+  return (mv_word<false>(m, y, x >> 5) >> (x & 31)) & 1u;
 }
 
 // direction codes as OpenCV: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE
@@ -589,6 +596,7 @@ struct Contour {
 // is either the component's outer border seen from a later "tip", or the border of a hole).
 // When (px,py) is given (px >= 0) the even-odd crossing number of the closed polygon with respect to that
 // lattice point is returned in *inside.
+template <bool kWin>
 __device__ Contour trace_border(const MaskView& m, int x0, int y0, int px, int py, bool* inside) {
   Contour c;
   c.a00 = c.a10 = c.a01 = 0;
@@ -599,7 +607,7 @@ __device__ Contour trace_border(const MaskView& m, int x0, int y0, int px, int p
   int s = 4, s_end = 4;
   do {
     s = (s - 1) & 7;
-    if (mv_bit(m, x0 + dir_dx(s), y0 + dir_dy(s))) break;
+    if (mv_bit<kWin>(m, x0 + dir_dx(s), y0 + dir_dy(s))) break;
   } while (s != s_end);
   if (s == s_end) {   // isolated pixel: one-point contour, all sums zero
     if (inside) *inside = false;
@@ -617,7 +625,7 @@ __device__ Contour trace_border(const MaskView& m, int x0, int y0, int px, int p
       s = (s + 1) & 7;
       nx = cx + dir_dx(s);
       ny = cy + dir_dy(s);
-    } while (!mv_bit(m, nx, ny));
+    } while (!mv_bit<kWin>(m, nx, ny));
     // emit (cx,cy)
     if (have_prev) {
       long long dxy = (long long)prevx * cy - (long long)cx * prevy;
@@ -653,11 +661,12 @@ __device__ Contour trace_border(const MaskView& m, int x0, int y0, int px, int p
 }
 
 // candidate starts in word wi of row y: foreground pixels whose W, NW, N and NE neighbours are background
+template <bool kWin>
 __device__ __forceinline__ uint32_t candidate_bits(const MaskView& m, int y, int wi) {
-  uint32_t cur = mv_word(m, y, wi);
+  uint32_t cur = mv_word<kWin>(m, y, wi);
   if (!cur) return 0u;
-  uint32_t curL = mv_word(m, y, wi - 1);
-  uint32_t up = mv_word(m, y - 1, wi), upL = mv_word(m, y - 1, wi - 1), upR = mv_word(m, y - 1, wi + 1);
+  uint32_t curL = mv_word<kWin>(m, y, wi - 1);
+  uint32_t up = mv_word<kWin>(m, y - 1, wi), upL = mv_word<kWin>(m, y - 1, wi - 1), upR = mv_word<kWin>(m, y - 1, wi + 1);
   uint32_t Wn = (cur << 1) | (curL >> 31);
   uint32_t NW = (up << 1) | (upL >> 31);
   uint32_t NE = (up >> 1) | (upR << 31);
@@ -666,13 +675,14 @@ __device__ __forceinline__ uint32_t candidate_bits(const MaskView& m, int y, int
 
 // Is the component starting at (px,py) enclosed by another component?  (RETR_EXTERNAL drops it then.)
 // Fast exits: a clear axis ray from the start pixel to the ROI edge proves it is not enclosed.
+template <bool kWin>
 __device__ bool is_enclosed(const MaskView& m, int px, int py) {
   // left / right rays in the same row
   {
     bool blocked_l = false, blocked_r = false;
     int wi0 = px >> 5, b = px & 31;
     for (int wi = 0; wi <= wi0 && !blocked_l; ++wi) {
-      uint32_t v = mv_word(m, py, wi);
+      uint32_t v = mv_word<kWin>(m, py, wi);
       if (wi == wi0) v &= (b == 0) ? 0u : (0xffffffffu >> (32 - b));
       blocked_l = v != 0;
     }
@@ -680,7 +690,7 @@ __device__ bool is_enclosed(const MaskView& m, int px, int py) {
     // right ray, word-wise: skip the component's own run that starts at px, then look for any further foreground
     bool in_run = true;
     for (int wi = wi0; wi < m.wpr && !blocked_r; ++wi) {
-      uint32_t v = mv_word(m, py, wi);
+      uint32_t v = mv_word<kWin>(m, py, wi);
       int lo = (wi == wi0) ? b : 0;                       // first bit of interest in this word
       v = (lo ? (v >> lo) : v);
       int nbits = 32 - lo;
@@ -708,7 +718,7 @@ __device__ bool is_enclosed(const MaskView& m, int px, int py) {
         while (fl && !blocked_u) {
           const int r = 31 - __clz(fl);
           fl &= ~(1u << r);
-          blocked_u = mv_bit(m, px, s * kTileRows + r);
+          blocked_u = mv_bit<kWin>(m, px, s * kTileRows + r);
         }
       }
     }
@@ -727,12 +737,12 @@ __device__ bool is_enclosed(const MaskView& m, int px, int py) {
       int y = s * kTileRows + r;
       if (y >= py) break;
       for (int wi = 0; wi < m.wpr; ++wi) {
-        uint32_t cand = candidate_bits(m, y, wi);
+        uint32_t cand = candidate_bits<kWin>(m, y, wi);
         while (cand) {
           int b = __ffs(cand) - 1;
           cand &= cand - 1;
           bool inside = false;
-          Contour c = trace_border(m, wi * 32 + b, y, px, py, &inside);
+          Contour c = trace_border<kWin>(m, wi * 32 + b, y, px, py, &inside);
           if (c.status == 1 && inside) return true;
         }
       }
@@ -752,6 +762,7 @@ __device__ __forceinline__ void undistort_point(const DevCamera& cam, float sx, 
   if (cam.nD > 0) {
     const double* k = cam.D;
     double x0 = x, y0 = y;
+#pragma unroll 1
     for (int j = 0; j < 5; ++j) {
       double r2 = x * x + y * y;
       double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
@@ -804,6 +815,7 @@ __host__ __device__ inline size_t k1b_scratch_stride(int flags_cap, int rows_cap
 constexpr int kK1bWindowMaxFrames = 64;
 constexpr int kK1bWindowWords = 8192;       // 32 KB per frame-warp: e.g. a 256 x 1024 px ROI; larger ROIs read the global mask
 
+template <bool kWin>
 __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane) {
   __syncwarp();
   int n = min(ws.n_cand, kCandCap);
@@ -811,9 +823,9 @@ __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Ro
     int i = base + lane;
     if (i < n) {
       int x0 = ws.cand_x[i], y0 = ws.cand_y[i];
-      Contour c = trace_border(m, x0, y0, -1, -1, nullptr);
+      Contour c = trace_border<kWin>(m, x0, y0, -1, -1, nullptr);
       if (c.status == -1) atomicOr(&ws.flags, MPE_F_TRACE_ABORT);
-      if (c.status == 1 && !is_enclosed(m, x0, y0)) {
+      if (c.status == 1 && !is_enclosed<kWin>(m, x0, y0)) {
         // led_detector.cpp:67-81
         double area = fabs((double)c.a00) * 0.5;                       // cv::contourArea
         int rw = c.maxx - c.minx + 1, rh = c.maxy - c.miny + 1;      // cv::boundingRect
@@ -853,12 +865,44 @@ __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Ro
   __syncwarp();
 }
 
+// contour-start candidates: one lane per foreground row, then lane-parallel border following
+template <bool kWin>
+__device__ __forceinline__ void find_candidates_and_trace(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane, int roi_wpr) {
+  const int rows_cap = ws.rows_cap;
+  const int n_rows = min(ws.n_rows, rows_cap);
+  for (int base = 0; base < n_rows; base += 32) {
+    if (base + lane < n_rows) {
+      const int y = ws.rows[base + lane];
+      // non-zero words of the row first (independent loads), then the neighbourhood test only where needed
+      unsigned long long nz = 0;
+      for (int wi = 0; wi < roi_wpr; ++wi)
+        if (mv_word<kWin>(m, y, wi)) nz |= 1ull << (wi & 63);
+      for (int wi = 0; wi < roi_wpr; ++wi) {
+        if (roi_wpr <= 64 && !((nz >> wi) & 1ull)) continue;
+        uint32_t cand = candidate_bits<kWin>(m, y, wi);
+        while (cand) {
+          int bbit = __ffs(cand) - 1;
+          cand &= cand - 1;
+          int slot = atomicAdd(&ws.n_cand, 1);
+          if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + bbit; ws.cand_y[slot] = y; }
+          else atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
+        }
+      }
+    }
+    __syncwarp();
+    if (ws.n_cand >= kCandCap / 2) process_candidates<kWin>(m, a, roi, ws, lane);
+  }
+  if (ws.n_cand > 0) process_candidates<kWin>(m, a, roi, ws, lane);
+  __syncwarp();
+}
+
 // latency bound (dependent mask loads while following a border): occupancy pays.  Eight CTAs per SM = 64 registers per thread and
 // a per-launch sized scratch; measured @8192 frames: 103 registers / 4 CTAs 0.271 ms, 80 / 6 0.220 ms, 64 / 8 0.195 ms
 #ifndef MPE_K1B_MINBLOCKS
 #define MPE_K1B_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extract_blobs_kernel(const K1bArgs a, int win_words) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t k1b_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kBlobWarpsPerCta + warp;
@@ -911,41 +955,30 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extr
     uint32_t* win = reinterpret_cast<uint32_t*>(my + sizeof(WarpScratch) + (size_t)flags_cap * 4 + (((size_t)rows_cap * 2 + 3) & ~(size_t)3));
     for (int i = lane; i < roi.h * roi_wpr; i += 32) win[i] = 0u;
     __syncwarp();
-    const int nr = ws.n_rows;
-    for (int i = lane; i < nr * roi_wpr; i += 32) {
-      const int y = ws.rows[i / roi_wpr], wi = i - (i / roi_wpr) * roi_wpr;
-      win[y * roi_wpr + wi] = mv_word(m, y, wi);
+    const int total = ws.n_rows * roi_wpr;
+    for (int base = 0; base < total; base += 32 * 8) {          // eight independent loads per lane in flight, then the stores
+      uint32_t v[8];
+      int at[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 32 + lane;
+        at[u] = -1; v[u] = 0u;
+        if (i < total) {
+          const int y = ws.rows[i / roi_wpr], wi = i - (i / roi_wpr) * roi_wpr;
+          at[u] = y * roi_wpr + wi;
+          v[u] = mv_word<false>(m, y, wi);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (at[u] >= 0) win[at[u]] = v[u];
     }
     __syncwarp();
     m.win = win; m.win_wpr = roi_wpr;
   }
 
-  // ---- contour-start candidates: one lane per foreground row, then lane-parallel border following
-  const int n_rows = min(ws.n_rows, rows_cap);
-  for (int base = 0; base < n_rows; base += 32) {
-    if (base + lane < n_rows) {
-      const int y = ws.rows[base + lane];
-      // non-zero words of the row first (independent loads), then the neighbourhood test only where needed
-      unsigned long long nz = 0;
-      for (int wi = 0; wi < roi_wpr; ++wi)
-        if (mv_word(m, y, wi)) nz |= 1ull << (wi & 63);
-      for (int wi = 0; wi < roi_wpr; ++wi) {
-        if (roi_wpr <= 64 && !((nz >> wi) & 1ull)) continue;
-        uint32_t cand = candidate_bits(m, y, wi);
-        while (cand) {
-          int bbit = __ffs(cand) - 1;
-          cand &= cand - 1;
-          int slot = atomicAdd(&ws.n_cand, 1);
-          if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + bbit; ws.cand_y[slot] = y; }
-          else atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
-        }
-      }
-    }
-    __syncwarp();
-    if (ws.n_cand >= kCandCap / 2) process_candidates(m, a, roi, ws, lane);
-  }
-  if (ws.n_cand > 0) process_candidates(m, a, roi, ws, lane);
-  __syncwarp();
+  if (m.win) find_candidates_and_trace<true>(m, a, roi, ws, lane, roi_wpr);
+  else find_candidates_and_trace<false>(m, a, roi, ws, lane, roi_wpr);
 
   // ---- order: cv::findContours returns the contours in reverse raster order of their start pixels ----
   const int n = min(ws.n_kept, MPE_MAX_BLOBS);
@@ -977,8 +1010,7 @@ cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
     cudaError_t e = ensure_dynamic_smem(extract_blobs_kernel, smem, configured);
     if (e != cudaSuccess) return e;
   }
-  extract_blobs_kernel<<<grid, 32 * kBlobWarpsPerCta, smem, st>>>(a, win_words);
-  return cudaGetLastError();
+  return launch_k(extract_blobs_kernel, grid, 32 * kBlobWarpsPerCta, smem, st, a, win_words);
 }
 
 }  // namespace mpe

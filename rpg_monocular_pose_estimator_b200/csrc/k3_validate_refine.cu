@@ -295,6 +295,7 @@ struct CheckFrame {
 };
 
 __global__ void __launch_bounds__(kK3aThreads) check_kernel(const K3Args a, int G, int Nmax) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t k3_smem[];
   const int n_obj = a.pp.n_obj;
   CheckFrame* fr = reinterpret_cast<CheckFrame*>(k3_smem);
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(kK3aThreads) check_kernel(const K3Args a, int 
 constexpr int kWideThreads = 128;     // 4 warps = the 4 P3P solutions
 
 __global__ void __launch_bounds__(kWideThreads) check_wide_kernel(const K3Args a) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t k3w_smem[];
   const int n_obj = a.pp.n_obj;
   CheckFrame& F = *reinterpret_cast<CheckFrame*>(k3w_smem);
@@ -618,6 +620,7 @@ __global__ void __launch_bounds__(kWideThreads) check_wide_kernel(const K3Args a
 constexpr int kK3bThreads = 64;
 
 __global__ void __launch_bounds__(kK3bThreads) refine_kernel(const K3Args a) {
+  pdl_enter();
   const int f = blockIdx.x * kK3bThreads + threadIdx.x;
   if (f >= a.n_frames) return;
   if (a.active && !a.active[f]) return;
@@ -772,6 +775,7 @@ __device__ __forceinline__ uint32_t nib_swap(uint32_t pk, int i, int j) {
 
 template <int G>
 __global__ void __launch_bounds__(kGnThreads) gauss_newton_kernel(const K3Args a, int gate_on_ok) {
+  pdl_enter();
   constexpr int kGroups = kGnThreads / G;
   __shared__ GnScratch scratch[kGroups];
   const int gid = threadIdx.x / G, gl = threadIdx.x % G;
@@ -1043,8 +1047,7 @@ cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
   if ((a.mode == 0 || a.mode == 1) && a.n_frames <= kGnCooperativeMaxFrames && wide_ok()) {
     const int n_obj = a.pp.n_obj;
     size_t smem = sizeof(CheckFrame) + 4 * 32 * (sizeof(double) + sizeof(int)) + (size_t)32 * n_obj * 3 * sizeof(double) + 32 * sizeof(int);
-    check_wide_kernel<<<a.n_frames, kWideThreads, smem, st>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(check_wide_kernel, a.n_frames, kWideThreads, smem, st, a);
     if (e != cudaSuccess) return e;
   } else if (a.mode == 0 || a.mode == 1) {
     const int n_obj = a.pp.n_obj;
@@ -1058,8 +1061,7 @@ cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
     }
     int grid = (a.n_frames + G - 1) / G;
-    check_kernel<<<grid, kK3aThreads, smem, st>>>(a, G, Nmax);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(check_kernel, grid, kK3aThreads, smem, st, a, G, Nmax);
     if (e != cudaSuccess) return e;
   }
   // Gauss-Newton layout.  Measured on B200: one frame takes 105 us with a thread per frame and 36.5 us with 32 lanes per frame,
@@ -1070,23 +1072,20 @@ cudaError_t launch_validate_refine(const K3Args& a, cudaStream_t st) {
   if (gn_mode < 0) { const char* e = getenv("MPE_K3_GN"); gn_mode = e ? atoi(e) : -2; }
   const bool cooperative = (gn_mode == 8 || gn_mode == 32) || (gn_mode != 0 && a.n_frames <= kGnCooperativeMaxFrames);
   if (!cooperative || a.mode == 1) {
-    refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(refine_kernel, (a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st, a);
   }
   // mode 0: acceptance test + Kabsch with a thread per frame (refine_kernel in check-only mode), then the lane-cooperative
   // Gauss-Newton for the frames it accepted; mode 2: Gauss-Newton only
   if (a.mode == 0) {
     K3Args chk = a;
     chk.mode = 1;
-    refine_kernel<<<(a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st>>>(chk);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(refine_kernel, (a.n_frames + kK3bThreads - 1) / kK3bThreads, kK3bThreads, 0, st, chk);
     if (e != cudaSuccess) return e;
   }
   const int gate = (a.mode == 0) ? 1 : 0;
   const int lanes = (gn_mode == 8) ? 8 : 32;
-  if (lanes == 32) gauss_newton_kernel<32><<<(a.n_frames + 1) / 2, kGnThreads, 0, st>>>(a, gate);
-  else gauss_newton_kernel<8><<<(a.n_frames + 7) / 8, kGnThreads, 0, st>>>(a, gate);
-  return cudaGetLastError();
+  if (lanes == 32) return launch_k(gauss_newton_kernel<32>, (a.n_frames + 1) / 2, kGnThreads, 0, st, a, gate);
+  return launch_k(gauss_newton_kernel<8>, (a.n_frames + 7) / 8, kGnThreads, 0, st, a, gate);
 }
 
 }  // namespace mpe

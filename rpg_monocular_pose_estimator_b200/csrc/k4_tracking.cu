@@ -18,6 +18,7 @@ namespace {
 
 // ---- step 1: predictWithROI (or the cold-branch preamble) ---------------------------------------------------------
 __global__ void track_begin_kernel(const TrackArgs a) {
+  pdl_enter();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n) return;
   StreamState& st = a.state[s];
@@ -129,6 +130,7 @@ __device__ __forceinline__ void track_after_detect_body(const TrackArgs& a, int 
 }
 
 __global__ void track_after_detect_kernel(const TrackArgs a, int pass) {
+  pdl_enter();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n) return;
   track_after_detect_body(a, pass, s);
@@ -137,6 +139,7 @@ __global__ void track_after_detect_kernel(const TrackArgs a, int pass) {
 // pass 0 wrapper: afterwards the ROI of every stream that does not retry is emptied, so that the retry launches of K1 find no
 // tile to work on for it
 __global__ void track_after_detect0_kernel(const TrackArgs a) {
+  pdl_enter();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n) return;
   track_after_detect_body(a, 0, s);
@@ -147,9 +150,7 @@ __global__ void track_after_detect0_kernel(const TrackArgs a) {
 //  optimisePose" — are written by the check kernel's epilogue: K3Args::set_gn_if_ok / set_init_if_fail.)
 
 // ---- step 5: optimiseAndUpdatePose bookkeeping (:802-812, :794-800) + result records ------------------------------
-__global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.n) return;
+__device__ __forceinline__ void track_finish_body(const TrackArgs& a, mpe_result* out, int s) {
   StreamState& st = a.state[s];
   // short step: this stream needs a stage the short step does not contain (cold start, whole-image retry, re-initialisation) -> state
   // untouched, the host repeats the step in full (track_begin recomputes the same prediction from the unchanged poses)
@@ -185,6 +186,24 @@ __global__ void track_finish_kernel(const TrackArgs a, mpe_result* out) {
   out[s] = r;
 }
 
+// out_host (optional): a second copy of the records, written by the whole CTA straight into page-locked host memory — for a few
+// cameras that replaces the device-to-host copy that would follow.
+__global__ void track_finish_kernel(const TrackArgs a, mpe_result* out, mpe_result* out_host) {
+  pdl_enter();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < a.n) track_finish_body(a, out, s);
+  if (out_host) {
+    static_assert(sizeof(mpe_result) % 8 == 0, "record copied in 8-byte words");
+    __syncthreads();
+    const int s0 = blockIdx.x * blockDim.x;
+    const int cnt = min((int)blockDim.x, a.n - s0);
+    const size_t words = (size_t)max(cnt, 0) * (sizeof(mpe_result) / 8);
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(out + s0);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(out_host + s0);
+    for (size_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  }
+}
+
 __global__ void track_reset_kernel(StreamState* st, int n) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -197,13 +216,14 @@ __global__ void track_reset_kernel(StreamState* st, int n) {
 
 static inline int grid_for(int n) { return (n + 127) / 128; }
 
-cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st) { track_begin_kernel<<<grid_for(a.n), 128, 0, st>>>(a); return cudaGetLastError(); }
+cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st) { return launch_k(track_begin_kernel, grid_for(a.n), 128, 0, st, a); }
 cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st) {
-  if (pass == 0) track_after_detect0_kernel<<<grid_for(a.n), 128, 0, st>>>(a);
-  else track_after_detect_kernel<<<grid_for(a.n), 128, 0, st>>>(a, pass);
-  return cudaGetLastError();
+  if (pass == 0) return launch_k(track_after_detect0_kernel, grid_for(a.n), 128, 0, st, a);
+  return launch_k(track_after_detect_kernel, grid_for(a.n), 128, 0, st, a, pass);
 }
-cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st) { track_finish_kernel<<<grid_for(a.n), 128, 0, st>>>(a, out); return cudaGetLastError(); }
+cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, mpe_result* out_host, cudaStream_t st) {
+  return launch_k(track_finish_kernel, grid_for(a.n), 128, 0, st, a, out, out_host);
+}
 cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st) { track_reset_kernel<<<grid_for(n), 128, 0, st>>>(s, n); return cudaGetLastError(); }
 
 }  // namespace mpe

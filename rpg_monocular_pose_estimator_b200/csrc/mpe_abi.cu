@@ -14,6 +14,8 @@
 
 using namespace mpe;
 
+namespace mpe { thread_local bool tl_pdl = false; }
+
 namespace {
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -76,6 +78,8 @@ struct mpe_ctx {
   bool pipeline = false;           // split large cold batches over two streams: measured SLOWER (3.06 vs 2.80 ms @8192); MPE_PIPELINE=1 enables
   DevBuffers d;
   mpe_result* h_results = nullptr;   // pinned
+  double* h_times = nullptr;         // pinned: time stamps read in place by the tracking step of a few cameras
+  mpe_result* h_results_dev = nullptr; const double* h_times_dev = nullptr;   // their device aliases
   // configuration
   bool have_camera = false, have_markers = false, have_params = false;
   DevCamera cam{};
@@ -83,6 +87,7 @@ struct mpe_ctx {
   mpe_params params{};
   // instrumentation
   bool timing = false;
+  bool mapped_io = true;             // MPE_MAPPED_IO=0 switches the in-place time stamps / records of small steps off
   cudaEvent_t ev[10]{};
   bool timing_pending = false;
   long long launches = 0;
@@ -238,8 +243,33 @@ int encode_tensor_map(mpe_ctx* c, const FrameSource& src, int box_w, int rows, C
   return MPE_OK;
 }
 
+// MPE_STEP_TRACE=1 (diagnostic, plain launches only): CUDA events between the stages of the tracking step; the previous step's
+// stage times are printed to stderr when the next step starts.
+struct StepTrace {
+  static constexpr int kMax = 32;
+  cudaEvent_t ev[kMax]; const char* name[kMax]; int n = 0; bool made = false; int on = -1; bool pending = false;
+  bool enabled() { if (on < 0) { const char* e = getenv("MPE_STEP_TRACE"); on = (e && atoi(e)) ? 1 : 0; } return on == 1; }
+  void begin(cudaStream_t st) {
+    if (!enabled()) return;
+    if (!made) { for (auto& e : ev) cudaEventCreate(&e); made = true; }
+    if (pending) {
+      cudaEventSynchronize(ev[n - 1]);
+      fprintf(stderr, "[step trace]");
+      for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s %.1f", name[i], ms * 1e3f); }
+      float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev[n - 1]); fprintf(stderr, " | total %.1f us\n", tot * 1e3f);
+    }
+    n = 0; pending = true; mark("begin", st);
+  }
+  void mark(const char* what, cudaStream_t st) { if (!enabled() || n >= kMax) return; name[n] = what; cudaEventRecord(ev[n++], st); }
+};
+static StepTrace g_trace;
+
 void time_begin(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) cudaEventRecord(c->ev[2 * k], st); }
-void time_end(mpe_ctx* c, int k, cudaStream_t st) { if (c->timing) { cudaEventRecord(c->ev[2 * k + 1], st); c->timing_pending = true; } }
+void time_end(mpe_ctx* c, int k, cudaStream_t st) {
+  if (c->timing) { cudaEventRecord(c->ev[2 * k + 1], st); c->timing_pending = true; }
+  static const char* const kStage[5] = {"scan", "extract", "sweep", "check/refine", "blur"};
+  if (g_trace.pending) g_trace.mark(kStage[k], st);
+}
 
 // K1a + K1b over frames [f0, f0+n) of `src`, outputs into slots [slot0, slot0+n) of the context buffers.
 int run_find_leds(mpe_ctx* c, const FrameSource& src, int f0, int n, int slot0, Roi roi, const Roi* rois_dev, cudaStream_t st,
@@ -525,6 +555,7 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(dev_alloc(&c->d.triples, (size_t)kTripleFields * kMaxPerms));
   { const char* e = getenv("MPE_K2_NO_FILTER"); if (e && e[0] == '1') c->k2_filter = 0; }
   { const char* e = getenv("MPE_SHORT_STEPS"); if (e && e[0] == '0') c->short_steps = false; }
+  { const char* e = getenv("MPE_MAPPED_IO"); if (e && e[0] == '0') c->mapped_io = false; }
   { const char* e = getenv("MPE_K2_FILTER"); if (e && e[0] >= '0' && e[0] <= '2') c->k2_filter = e[0] - '0'; }
   CREATE_TRY(dev_alloc(&c->d.corr, B * 2 * MPE_MAX_LEDS));
   CREATE_TRY(dev_alloc(&c->d.n_corr, B));
@@ -556,6 +587,13 @@ int mpe_create(mpe_ctx** out, int device, int max_batch, int max_width, int max_
   CREATE_TRY(cudaMemset(c->d.corr, 0, B * 2 * MPE_MAX_LEDS * sizeof(uint32_t)));
   CREATE_TRY(cudaMemset(c->d.rowflags, 0, B * c->flags_per_frame * sizeof(uint32_t)));
   CREATE_TRY(cudaMallocHost((void**)&c->h_results, B * sizeof(mpe_result)));
+  CREATE_TRY(cudaMallocHost((void**)&c->h_times, B * sizeof(double)));
+  {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, c->h_results, 0) == cudaSuccess) c->h_results_dev = (mpe_result*)dp; else cudaGetLastError();
+    dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, c->h_times, 0) == cudaSuccess) c->h_times_dev = (const double*)dp; else cudaGetLastError();
+  }
   for (int i = 0; i < 10; ++i) CREATE_TRY(cudaEventCreate(&c->ev[i]));
   // PoseEstimator::PoseEstimator() defaults (pose_estimator.cpp:36-39)
   c->pp.back_projection_pixel_tolerance = 3;
@@ -582,6 +620,7 @@ void mpe_destroy(mpe_ctx* c) {
   cudaFree(c->d.updated); cudaFree(c->d.rois); cudaFree(c->d.results); cudaFree(c->d.check_sums); cudaFree(c->d.check_cnt); cudaFree(c->d.hot_tiles); cudaFree(c->d.pool); cudaFree(c->d.counters); cudaFree(c->d.tile_list); cudaFree(c->d.tile_count); cudaFree(c->d.k2_list); cudaFree(c->d.k2_count); cudaFree(c->d.streams); cudaFree(c->d.result_rois);
   cudaFree(c->d.pred_px); cudaFree(c->d.masks); cudaFree(c->d.track_flags); cudaFree(c->d.times);
   if (c->h_results) cudaFreeHost(c->h_results);
+  if (c->h_times) cudaFreeHost(c->h_times);
   for (int i = 0; i < 10; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->chunk_events) cudaEventDestroy(e);
   for (int gi = 0; gi < 2; ++gi) if (c->graph_exec[gi]) cudaGraphExecDestroy(c->graph_exec[gi]);
@@ -1001,12 +1040,13 @@ int mpe_streams_set_frame_map(mpe_ctx* c, const int* frame_index_device, int n_f
 }
 
 // Enqueues one estimateBodyPose step (pose_estimator.cpp:62-147) for n streams on `st`; the time stamps are already in c->d.times.
-static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st, bool fast) {
+constexpr int kPdlMaxStreams = 64;
+static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaStream_t st, bool fast, bool mapped_io) {
   const int width = src.width, height = src.height;
   const size_t B = (size_t)c->max_batch;
   TrackArgs t{};
   t.n = n; t.img_w = width; t.img_h = height; t.roi_border = c->params.roi_border_thickness;
-  t.state = c->d.streams; t.times = c->d.times; t.cam = c->cam; t.pp = c->pp;
+  t.state = c->d.streams; t.times = mapped_io ? c->h_times_dev : c->d.times; t.cam = c->cam; t.pp = c->pp;
   t.rois = c->d.rois; t.result_rois = c->d.result_rois; t.pred_px = c->d.pred_px;
   t.mode = c->d.masks; t.done = c->d.masks + B; t.a_retry = c->d.masks + 2 * B; t.a_check = c->d.masks + 3 * B;
   t.a_init = c->d.masks + 4 * B; t.a_gn = c->d.masks + 5 * B;
@@ -1016,10 +1056,18 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   t.corr = c->d.corr; t.n_corr = c->d.n_corr; t.pose_io = c->d.pose; t.cov = c->d.cov; t.ok = c->d.ok; t.iters = c->d.iters; t.updated = c->d.updated;
   Roi full{0, 0, width, height};
   int rc;
+  // few cameras: programmatic dependent launches hide the launch latency between the step's small kernels (mpe_internal.cuh)
+  static int pdl_env = -1;
+  if (pdl_env < 0) { const char* e = getenv("MPE_PDL"); pdl_env = e ? atoi(e) : 1; }
+  PdlScope pdl(pdl_env != 0 && n <= kPdlMaxStreams);
+  g_trace.begin(st);
   CUDA_TRY(c, launch_track_begin(t, st));                                                        // predictWithROI
+  g_trace.mark("predict", st);
   rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, nullptr);   // findLeds(ROI)
   if (rc != MPE_OK) return rc;
+  g_trace.mark("findLeds", st);
   CUDA_TRY(c, launch_track_after_detect(t, 0, st));                                              // + empties the ROI of streams that do not retry
+  g_trace.mark("match", st);
   if (!fast) {
     rc = run_find_leds(c, src, 0, n, 0, full, c->d.rois, st, kTrackTileWidthPx, c->frame_map, t.a_retry);  // whole-image retry (only where needed)
     if (rc != MPE_OK) return rc;
@@ -1028,6 +1076,7 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   }
   rc = run_refine(c, 0, n, 1, st, t.a_check, t.a_gn, t.a_init);                                  // checkCorrespondences on the NN matches; ok -> GN, else -> initialise()
   if (rc != MPE_OK) return rc;
+  g_trace.mark("check+kabsch", st);
   if (!fast) {
     rc = run_sweep(c, 0, n, st, t.a_init);                                                       // initialise(): cold streams + failed checks
     if (rc != MPE_OK) return rc;
@@ -1036,7 +1085,9 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
   }
   rc = run_refine(c, 0, n, 2, st, t.a_gn);                                                       // optimisePose
   if (rc != MPE_OK) return rc;
-  CUDA_TRY(c, launch_track_finish(t, c->d.results, st));
+  g_trace.mark("gauss-newton", st);
+  CUDA_TRY(c, launch_track_finish(t, c->d.results, mapped_io ? c->h_results_dev : nullptr, st));
+  g_trace.mark("finish", st);
   c->launches += 3;
   return MPE_OK;
 }
@@ -1047,29 +1098,34 @@ static int enqueue_streams_step(mpe_ctx* c, const FrameSource& src, int n, cudaS
 static int run_streams_step(mpe_ctx* c, const FrameSource& src, int n, const double* times, bool fetch, bool fast = false) {
   const int gi = fast ? 1 : 0;
   cudaStream_t st = c->stream;
-  CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  // A few cameras whose records the caller waits for: the time stamps are read, and the records written, in place in page-locked
+  // host memory — no copy operations around the step (the step is synchronised before the call returns, see finish_step).
+  const bool mapped_io = fetch && n <= kPdlMaxStreams && c->mapped_io && c->h_times_dev && c->h_results_dev;
+  if (mapped_io) std::memcpy(c->h_times, times, (size_t)n * sizeof(double));
+  else CUDA_TRY(c, cudaMemcpyAsync(c->d.times, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  const bool copy_back = fetch && !mapped_io;
   if (!c->use_graphs || c->timing) {
-    int rc = enqueue_streams_step(c, src, n, st, fast);
+    int rc = enqueue_streams_step(c, src, n, st, fast, mapped_io);
     if (rc != MPE_OK) return rc;
-    if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
+    if (copy_back) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
     return MPE_OK;
   }
-  mpe_ctx::StepGraphKey key{src.base, src.pitch, src.frame_stride, src.width, src.height, n, c->frame_map, c->frame_map_total, fetch ? 1 : 0,
+  mpe_ctx::StepGraphKey key{src.base, src.pitch, src.frame_stride, src.width, src.height, n, c->frame_map, c->frame_map_total, (fetch ? 1 : 0) | (mapped_io ? 2 : 0),
                             c->cfg_version, st};
   if (!c->graph_exec[gi] || !(key == c->graph_key[gi])) {
     if (!c->have_pending[gi] || !(key == c->pending_key[gi])) {      // first use of this key: plain launches
       c->pending_key[gi] = key; c->have_pending[gi] = true;
-      int rc = enqueue_streams_step(c, src, n, st, fast);
+      int rc = enqueue_streams_step(c, src, n, st, fast, mapped_io);
       if (rc != MPE_OK) return rc;
-      if (fetch) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
+      if (copy_back) CUDA_TRY(c, cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st));
       return MPE_OK;
     }
     if (c->graph_exec[gi]) { cudaGraphExecDestroy(c->graph_exec[gi]); c->graph_exec[gi] = nullptr; }
     const long long l0 = c->launches;
     CUDA_TRY(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_streams_step(c, src, n, st, fast);
+    int rc = enqueue_streams_step(c, src, n, st, fast, mapped_io);
     cudaError_t ce = cudaSuccess;
-    if (rc == MPE_OK && fetch) ce = cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st);
+    if (rc == MPE_OK && copy_back) ce = cudaMemcpyAsync(c->h_results, c->d.results, (size_t)n * sizeof(mpe_result), cudaMemcpyDeviceToHost, st);
     cudaGraph_t g = nullptr;
     cudaError_t ee = cudaStreamEndCapture(st, &g);
     if (rc != MPE_OK) { if (g) cudaGraphDestroy(g); return rc; }

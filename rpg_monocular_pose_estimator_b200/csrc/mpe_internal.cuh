@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <utility>
 #include "../../include/mpe_b200.h"
 
 namespace mpe {
@@ -44,6 +45,44 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemAttrCach
   }
   return cudaSuccess;
 }
+
+// ---- programmatic dependent launch for the latency path -------------------------------------------------------------------
+// A tracking step of a handful of cameras is ~10 tiny kernels, each a single dependent chain; between two of them the GPU
+// otherwise drains, then fetches and launches the next grid.  Launched with the programmatic-serialisation attribute the next
+// grid may be scheduled while its predecessor winds down; it blocks in pdl_enter() until the predecessor has COMPLETED and its
+// writes are visible, so the semantics are those of plain stream order.  Measured, one camera, graph replay: 167.9 -> 165.2 us
+// per image; plain launches 184 -> 170 us.  Releasing the dependents at kernel entry instead (MPE_PDL_EARLY=1, all grids of the
+// step resident at once) was SLOWER than no attribute at all (171.3 us), so the implicit trigger at grid exit is used.  Rules:
+//  * every kernel launched through launch_k() executes pdl_enter() before anything else, in every thread (a grid that finished
+//    without waiting would release its successor early);
+//  * the attribute is used for small launches only (tl_pdl): a big grid parked on the SMs would take slots from the running one.
+extern thread_local bool tl_pdl;
+struct PdlScope {
+  bool saved;
+  explicit PdlScope(bool on) : saved(tl_pdl) { tl_pdl = on; }
+  ~PdlScope() { tl_pdl = saved; }
+};
+#ifdef __CUDACC__
+#ifndef MPE_PDL_EARLY
+#define MPE_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if MPE_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = tl_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // Camera model as the kernels consume it.
 struct DevCamera {
@@ -200,7 +239,7 @@ struct TrackArgs {
 // ---- launchers (defined next to the kernels) ----
 cudaError_t launch_track_begin(const TrackArgs& a, cudaStream_t st);
 cudaError_t launch_track_after_detect(const TrackArgs& a, int pass, cudaStream_t st);
-cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, cudaStream_t st);
+cudaError_t launch_track_finish(const TrackArgs& a, mpe_result* out, mpe_result* out_host, cudaStream_t st);
 cudaError_t launch_track_reset(StreamState* s, int n, cudaStream_t st);
 cudaError_t launch_find_leds(const K1aArgs& a, const CUtensorMap& tmap, int radius, int n_sms, cudaStream_t st);
 cudaError_t launch_build_tile_list(const K1Geom& g, uint32_t* list, uint32_t* count, cudaStream_t st);
