@@ -56,6 +56,10 @@ def main():
     print("top source lines by executed instructions (share of instructions | share of stall samples):")
     for loc, v in per_line.most_common(top):
         print(f"  {v / tot * 100:5.2f} % | {per_line_s[loc] / max(tots, 1) * 100:5.2f} %  {loc[0]}:{loc[1]}")
+    if os.environ.get("BY_STALL"):      # BY_STALL=1: the same table ordered by stall samples
+        print("top source lines by stall samples (share of stall samples | share of instructions):")
+        for loc, v in per_line_s.most_common(top):
+            print(f"  {v / max(tots, 1) * 100:5.2f} % | {per_line[loc] / tot * 100:5.2f} %  {loc[0]}:{loc[1]}")
 
 if __name__ == "__main__":
     main()

@@ -791,16 +791,19 @@ constexpr int kBlobWarpsPerCta = 4;
 
 // Per-warp scratch.  The two variable parts are sized per launch (row flags: strips x column tiles of the geometry; row list: image
 // rows), so that small images keep the footprint small and more frame-warps share an SM.
+struct KeptList {                  // the blobs of one frame that passed the filters
+  int n_kept;
+  int flags;
+  int kept_key[MPE_MAX_BLOBS];     // raster index of the contour start (sort key)
+  float kept_cx[MPE_MAX_BLOBS];
+  float kept_cy[MPE_MAX_BLOBS];
+};
 struct WarpScratch {
   int cand_x[kCandCap];
   int cand_y[kCandCap];
   int n_cand;
-  int n_kept;
-  int flags;
   int n_rows;
-  int kept_key[MPE_MAX_BLOBS];     // raster index of the contour start (sort key)
-  float kept_cx[MPE_MAX_BLOBS];
-  float kept_cy[MPE_MAX_BLOBS];
+  KeptList kl;
   uint32_t* rowflags;              // [flags_cap]
   uint16_t* rows;                  // [rows_cap] rows of this frame that contain foreground
   int flags_cap, rows_cap;
@@ -813,7 +816,47 @@ __host__ __device__ inline size_t k1b_scratch_stride(int flags_cap, int rows_cap
 // Small launches (a handful of cameras: the latency case) copy the ROI's mask rows into shared memory first: the border follower
 // is a chain of dependent single-word reads, ~10x cheaper from shared memory than from L2.  Large batches keep the occupancy instead.
 constexpr int kK1bWindowMaxFrames = 64;
+constexpr int kK1bPoolMinFrames = 2048;    // from here on a warp serves four frames (extract_blobs_pooled_kernel)
 constexpr int kK1bWindowWords = 8192;       // 32 KB per frame-warp: e.g. a 256 x 1024 px ROI; larger ROIs read the global mask
+
+// One contour-start candidate: follow its border, drop holes / enclosed components, apply the blob filters (led_detector.cpp:67-81)
+template <bool kWin>
+__device__ __forceinline__ void process_one_candidate(const MaskView& m, const K1bArgs& a, const Roi roi, KeptList& kl, int x0, int y0) {
+  Contour c = trace_border<kWin>(m, x0, y0, -1, -1, nullptr);
+  if (c.status == -1) atomicOr(&kl.flags, MPE_F_TRACE_ABORT);
+  if (c.status == 1 && !is_enclosed<kWin>(m, x0, y0)) {
+    double area = fabs((double)c.a00) * 0.5;                       // cv::contourArea
+    int rw = c.maxx - c.minx + 1, rh = c.maxy - c.miny + 1;      // cv::boundingRect
+    // cv::moments(contour): m00 = a00 * (+-0.5), m10 = a10 * (+-1/6), m01 = a01 * (+-1/6), sign so that m00 > 0
+    double m00 = 0, m10 = 0, m01 = 0;
+    if (c.a00 != 0) {
+      double db1_2 = (c.a00 > 0) ? 0.5 : -0.5;
+      double db1_6 = (c.a00 > 0) ? 0.16666666666666666666666666666667 : -0.16666666666666666666666666666667;
+      m00 = (double)c.a00 * db1_2;
+      m10 = (double)c.a10 * db1_6;
+      m01 = (double)c.a01 * db1_6;
+    }
+    float mcx = (float)(m10 / m00) + (float)roi.x;                  // Point2f(m10/m00, m01/m00) + Point2f(ROI.x, ROI.y)
+    float mcy = (float)(m01 / m00) + (float)roi.y;
+    const double pi = 3.1415926535897932384626433832795;
+    double wh = fabs(1 - fmin((double)rw / (double)rh, (double)rh / (double)rw));
+    double hw2 = (double)(rw / 2), hh2 = (double)(rh / 2);          // integer division, led_detector.cpp:80-81
+    double cw = fabs(1 - (area / (pi * (hw2 * hw2))));
+    double ch = fabs(1 - (area / (pi * (hh2 * hh2))));
+    bool keep = area >= a.bp.min_blob_area && area <= a.bp.max_blob_area && wh <= a.bp.max_width_height_distortion &&
+                cw <= a.bp.max_circular_distortion && ch <= a.bp.max_circular_distortion;
+    if (keep) {
+      int slot = atomicAdd(&kl.n_kept, 1);
+      if (slot < MPE_MAX_BLOBS) {
+        kl.kept_key[slot] = y0 * m.w + x0;
+        kl.kept_cx[slot] = mcx;
+        kl.kept_cy[slot] = mcy;
+      } else {
+        atomicOr(&kl.flags, MPE_F_BLOB_OVERFLOW);
+      }
+    }
+  }
+}
 
 template <bool kWin>
 __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Roi roi, WarpScratch& ws, int lane) {
@@ -821,48 +864,40 @@ __device__ void process_candidates(const MaskView& m, const K1bArgs& a, const Ro
   int n = min(ws.n_cand, kCandCap);
   for (int base = 0; base < n; base += 32) {
     int i = base + lane;
-    if (i < n) {
-      int x0 = ws.cand_x[i], y0 = ws.cand_y[i];
-      Contour c = trace_border<kWin>(m, x0, y0, -1, -1, nullptr);
-      if (c.status == -1) atomicOr(&ws.flags, MPE_F_TRACE_ABORT);
-      if (c.status == 1 && !is_enclosed<kWin>(m, x0, y0)) {
-        // led_detector.cpp:67-81
-        double area = fabs((double)c.a00) * 0.5;                       // cv::contourArea
-        int rw = c.maxx - c.minx + 1, rh = c.maxy - c.miny + 1;      // cv::boundingRect
-        // cv::moments(contour): m00 = a00 * (+-0.5), m10 = a10 * (+-1/6), m01 = a01 * (+-1/6), sign so that m00 > 0
-        double m00 = 0, m10 = 0, m01 = 0;
-        if (c.a00 != 0) {
-          double db1_2 = (c.a00 > 0) ? 0.5 : -0.5;
-          double db1_6 = (c.a00 > 0) ? 0.16666666666666666666666666666667 : -0.16666666666666666666666666666667;
-          m00 = (double)c.a00 * db1_2;
-          m10 = (double)c.a10 * db1_6;
-          m01 = (double)c.a01 * db1_6;
-        }
-        float mcx = (float)(m10 / m00) + (float)roi.x;                  // Point2f(m10/m00, m01/m00) + Point2f(ROI.x, ROI.y)
-        float mcy = (float)(m01 / m00) + (float)roi.y;
-        const double pi = 3.1415926535897932384626433832795;
-        double wh = fabs(1 - fmin((double)rw / (double)rh, (double)rh / (double)rw));
-        double hw2 = (double)(rw / 2), hh2 = (double)(rh / 2);          // integer division, led_detector.cpp:80-81
-        double cw = fabs(1 - (area / (pi * (hw2 * hw2))));
-        double ch = fabs(1 - (area / (pi * (hh2 * hh2))));
-        bool keep = area >= a.bp.min_blob_area && area <= a.bp.max_blob_area && wh <= a.bp.max_width_height_distortion &&
-                    cw <= a.bp.max_circular_distortion && ch <= a.bp.max_circular_distortion;
-        if (keep) {
-          int slot = atomicAdd(&ws.n_kept, 1);
-          if (slot < MPE_MAX_BLOBS) {
-            ws.kept_key[slot] = y0 * m.w + x0;
-            ws.kept_cx[slot] = mcx;
-            ws.kept_cy[slot] = mcy;
-          } else {
-            atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
-          }
-        }
-      }
-    }
+    if (i < n) process_one_candidate<kWin>(m, a, roi, ws.kl, ws.cand_x[i], ws.cand_y[i]);
   }
   __syncwarp();
   if (lane == 0) ws.n_cand = 0;
   __syncwarp();
+}
+
+// kept blob i of a frame: its place in cv::findContours' output order (reverse raster order of the contour starts) and its
+// undistorted position (led_detector.cpp:97-110)
+__device__ __forceinline__ void emit_blob(const K1bArgs& a, const KeptList& kl, int f, int i, int n) {
+  const int key = kl.kept_key[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) rank += (kl.kept_key[j] > key) ? 1 : 0;
+  float ux, uy;
+  undistort_point(a.cam, kl.kept_cx[i], kl.kept_cy[i], &ux, &uy);
+  const size_t o = ((size_t)f * MPE_MAX_BLOBS + rank) * 2;
+  a.centers[o] = kl.kept_cx[i];
+  a.centers[o + 1] = kl.kept_cy[i];
+  a.det[o] = (double)ux;
+  a.det[o + 1] = (double)uy;
+}
+
+// The rows of a frame that contain foreground, from its row flags (order irrelevant: the blobs are sorted at the end)
+__device__ __forceinline__ void list_rows(const uint32_t* rowflags, int roi_strips, int n_ct, int roi_n_ct, int* n_rows, uint16_t* rows, int rows_cap, int lane) {
+  for (int s = lane; s < roi_strips; s += 32) {
+    uint32_t fl = 0;
+    for (int ct = 0; ct < roi_n_ct; ++ct) fl |= rowflags[s * n_ct + ct];
+    while (fl) {
+      int r = __ffs(fl) - 1;
+      fl &= fl - 1;
+      int slot = atomicAdd(n_rows, 1);
+      if (slot < rows_cap) rows[slot] = (uint16_t)(s * kTileRows + r);
+    }
+  }
 }
 
 // contour-start candidates: one lane per foreground row, then lane-parallel border following
@@ -875,8 +910,13 @@ __device__ __forceinline__ void find_candidates_and_trace(const MaskView& m, con
       const int y = ws.rows[base + lane];
       // non-zero words of the row first (independent loads), then the neighbourhood test only where needed
       unsigned long long nz = 0;
-      for (int wi = 0; wi < roi_wpr; ++wi)
-        if (mv_word<kWin>(m, y, wi)) nz |= 1ull << (wi & 63);
+      for (int w0 = 0; w0 < roi_wpr; w0 += 8) {                // eight loads in flight; a branch per loaded word would serialise them
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (w0 + u < roi_wpr) ? mv_word<kWin>(m, y, w0 + u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nz |= (unsigned long long)(v[u] != 0u) << ((w0 + u) & 63);
+      }
       for (int wi = 0; wi < roi_wpr; ++wi) {
         if (roi_wpr <= 64 && !((nz >> wi) & 1ull)) continue;
         uint32_t cand = candidate_bits<kWin>(m, y, wi);
@@ -885,7 +925,7 @@ __device__ __forceinline__ void find_candidates_and_trace(const MaskView& m, con
           cand &= cand - 1;
           int slot = atomicAdd(&ws.n_cand, 1);
           if (slot < kCandCap) { ws.cand_x[slot] = wi * 32 + bbit; ws.cand_y[slot] = y; }
-          else atomicOr(&ws.flags, MPE_F_BLOB_OVERFLOW);
+          else atomicOr(&ws.kl.flags, MPE_F_BLOB_OVERFLOW);
         }
       }
     }
@@ -924,21 +964,12 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extr
   const int roi_strips = (roi.h + kTileRows - 1) / kTileRows;
 
   // ---- cache the row flags of this frame; list the rows that contain foreground (order irrelevant: sorted at the end)
-  if (lane == 0) { ws.n_cand = 0; ws.n_kept = 0; ws.flags = 0; ws.n_rows = 0; }
+  if (lane == 0) { ws.n_cand = 0; ws.kl.n_kept = 0; ws.kl.flags = 0; ws.n_rows = 0; }
   __syncwarp();
   const uint32_t* gflags = a.rowflags + (size_t)f * g.flags_per_frame;
   for (int i = lane; i < roi_strips * g.n_ct && i < flags_cap; i += 32) ws.rowflags[i] = gflags[i];
   __syncwarp();
-  for (int s = lane; s < roi_strips; s += 32) {
-    uint32_t fl = 0;
-    for (int ct = 0; ct < roi_n_ct; ++ct) fl |= ws.rowflags[s * g.n_ct + ct];
-    while (fl) {
-      int r = __ffs(fl) - 1;
-      fl &= fl - 1;
-      int slot = atomicAdd(&ws.n_rows, 1);
-      if (slot < rows_cap) ws.rows[slot] = (uint16_t)(s * kTileRows + r);
-    }
-  }
+  list_rows(ws.rowflags, roi_strips, g.n_ct, roi_n_ct, &ws.n_rows, ws.rows, rows_cap, lane);
   __syncwarp();
 
   MaskView m;
@@ -981,26 +1012,192 @@ __global__ void __launch_bounds__(32 * kBlobWarpsPerCta, MPE_K1B_MINBLOCKS) extr
   else find_candidates_and_trace<false>(m, a, roi, ws, lane, roi_wpr);
 
   // ---- order: cv::findContours returns the contours in reverse raster order of their start pixels ----
-  const int n = min(ws.n_kept, MPE_MAX_BLOBS);
-  for (int i = lane; i < n; i += 32) {
-    int key = ws.kept_key[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (ws.kept_key[j] > key) ? 1 : 0;
-    float ux, uy;
-    undistort_point(a.cam, ws.kept_cx[i], ws.kept_cy[i], &ux, &uy);      // led_detector.cpp:97-110
-    size_t o = ((size_t)f * MPE_MAX_BLOBS + rank) * 2;
-    a.centers[o] = ws.kept_cx[i];
-    a.centers[o + 1] = ws.kept_cy[i];
-    a.det[o] = (double)ux;
-    a.det[o + 1] = (double)uy;
-  }
+  const int n = min(ws.kl.n_kept, MPE_MAX_BLOBS);
+  for (int i = lane; i < n; i += 32) emit_blob(a, ws.kl, f, i, n);
   if (lane == 0) {
     a.n_det[f] = n;
-    a.flags[f] = ws.flags;
+    a.flags[f] = ws.kl.flags;
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1b for large batches: one warp per GROUP of kPoolFrames frames.
+// A frame has ~5 contour-start candidates, so a warp that follows the borders of its own frame keeps ~6 of 32 lanes busy in
+// that phase and in the undistortion (measured @8192 frames: 6.7 active lanes per instruction, 133 M warp instructions, the
+// kernel latency bound with every resident warp working).  Pooling the candidates of a CTA's four frame-warps behind a block
+// barrier halved the instructions but left three of four warps waiting (0.204 -> 0.189 ms only).  Here every warp stays busy:
+// it lists rows and candidates frame by frame (lane = row), then follows the pooled candidates of its four frames with a lane
+// each, then undistorts the pooled blobs.  Same functions per candidate as the kernel above, hence identical results.
+// ------------------------------------------------------------------------------------------------
+// (frames per warp <= 4: two tag bits in the candidate word)
+template <int kPoolFrames>
+struct PoolScratch {
+  uint32_t cand[kCandCap];         // frame slot << 30 | y << 15 | x
+  int n_cand;
+  int n_rows;
+  KeptList kl[kPoolFrames];
+  MaskView mv[kPoolFrames];        // row flags read from global memory (the shared-memory copy is reused by the next frame)
+  Roi roi[kPoolFrames];
+};
+template <int kPoolFrames>
+__host__ __device__ inline size_t k1b_pool_stride(int flags_cap, int rows_cap) {
+  size_t n = sizeof(PoolScratch<kPoolFrames>) + (size_t)flags_cap * 4 + (((size_t)rows_cap * 2 + 3) & ~(size_t)3);
+  return (n + 15) & ~(size_t)15;
+}
+
+template <int kPoolFrames>
+__device__ void process_pooled(const K1bArgs& a, PoolScratch<kPoolFrames>& ps, int lane) {
+  __syncwarp();
+  const int n = min(ps.n_cand, kCandCap);
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    if (i < n) {
+      const uint32_t c = ps.cand[i];
+      const int q = (int)(c >> 30);
+      process_one_candidate<false>(ps.mv[q], a, ps.roi[q], ps.kl[q], (int)(c & 0x7fffu), (int)((c >> 15) & 0x7fffu));
+    }
+  }
+  __syncwarp();
+  if (lane == 0) ps.n_cand = 0;
+  __syncwarp();
+}
+
+#ifndef MPE_K1B_POOL_WARPS
+#define MPE_K1B_POOL_WARPS 4
+#endif
+#ifndef MPE_K1B_POOL_MINBLOCKS
+#define MPE_K1B_POOL_MINBLOCKS 8
+#endif
+// Measured @8192 frames of 752x480, two batches in flight (the headline) / the kernel alone:
+//   no pooling 5.59 M frames/s / 0.196 ms;  4 frames per warp, 4-warp CTAs, 64 registers 5.85 M / 0.213 ms;  3 frames 5.75 M / 0.169 ms;
+//   2 frames 5.69 M / 0.150 ms;  4 frames with 2-warp CTAs 5.78 M, with 1-warp CTAs 5.64 M (64 registers) / 5.62 M (95 registers).
+// Alone the kernel is a latency chain (four row scans, then one border-following pass), so fewer frames per warp finish sooner;
+// next to the other batch's kernels what counts is the issue slots and registers it leaves them: 71 M instead of 133 M warp
+// instructions.  The pipeline number decides.
+constexpr int kPoolWarpsPerCta = MPE_K1B_POOL_WARPS;
+template <int kPoolFrames>
+__global__ void __launch_bounds__(32 * kPoolWarpsPerCta, MPE_K1B_POOL_MINBLOCKS) extract_blobs_pooled_kernel(const K1bArgs a, int flags_cap) {
+  pdl_enter();
+  extern __shared__ __align__(16) uint8_t k1b_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const K1Geom& g = a.g;
+  const int f0 = (blockIdx.x * kPoolWarpsPerCta + warp) * kPoolFrames;
+  if (f0 >= g.n_frames) return;
+  const int rows_cap = g.mask_rows;
+  uint8_t* my = k1b_smem + (size_t)warp * k1b_pool_stride<kPoolFrames>(flags_cap, rows_cap);
+  PoolScratch<kPoolFrames>& ps = *reinterpret_cast<PoolScratch<kPoolFrames>*>(my);
+  uint32_t* rowflags = reinterpret_cast<uint32_t*>(my + sizeof(PoolScratch<kPoolFrames>));
+  uint16_t* rows = reinterpret_cast<uint16_t*>(my + sizeof(PoolScratch<kPoolFrames>) + (size_t)flags_cap * 4);
+  if (lane == 0) ps.n_cand = 0;
+  if (lane < kPoolFrames) { ps.kl[lane].n_kept = 0; ps.kl[lane].flags = 0; }
+  __syncwarp();
+
+  for (int q = 0; q < kPoolFrames; ++q) {
+    const int f = f0 + q;
+    if (f >= g.n_frames) break;                                // warp-uniform
+    if (a.active && !a.active[f]) continue;
+    const Roi roi = g.rois ? g.rois[f] : g.roi;
+    const int roi_wpr = (roi.w + 31) >> 5;
+    const int roi_n_ct = (roi.w + g.tw_px - 1) / g.tw_px;
+    const int roi_strips = (roi.h + kTileRows - 1) / kTileRows;
+    const uint32_t* gflags = a.rowflags + (size_t)f * g.flags_per_frame;
+    if (lane == 0) ps.n_rows = 0;
+    for (int i = lane; i < roi_strips * g.n_ct && i < flags_cap; i += 32) rowflags[i] = gflags[i];
+    __syncwarp();
+    list_rows(rowflags, roi_strips, g.n_ct, roi_n_ct, &ps.n_rows, rows, rows_cap, lane);
+    __syncwarp();
+
+    MaskView m;
+    m.flags = rowflags;
+    m.mask = a.mask + (size_t)f * g.mask_rows * g.mask_wpr;
+    m.w = roi.w; m.h = roi.h;
+    m.n_ct = g.n_ct;
+    m.roi_n_ct = roi_n_ct;
+    m.tw_px = g.tw_px;
+    m.wpr = g.mask_wpr;
+    m.words_per_ct = g.tw_px >> 5;
+    m.win = nullptr; m.win_wpr = 0;
+    if (lane == 0) {
+      ps.mv[q] = m;
+      ps.mv[q].flags = gflags;                                 // what the border follower of this frame reads later
+      ps.roi[q] = roi;
+    }
+    __syncwarp();
+
+    const int n_rows = min(ps.n_rows, rows_cap);
+    for (int base = 0; base < n_rows; base += 32) {
+      if (base + lane < n_rows) {
+        const int y = rows[base + lane];
+        unsigned long long nz = 0;
+        for (int w0 = 0; w0 < roi_wpr; w0 += 8) {              // eight loads in flight
+          uint32_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (w0 + u < roi_wpr) ? mv_word<false>(m, y, w0 + u) : 0u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) nz |= (unsigned long long)(v[u] != 0u) << ((w0 + u) & 63);
+        }
+        for (int wi = 0; wi < roi_wpr; ++wi) {
+          if (roi_wpr <= 64 && !((nz >> wi) & 1ull)) continue;
+          uint32_t cand = candidate_bits<false>(m, y, wi);
+          while (cand) {
+            const int bbit = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int slot = atomicAdd(&ps.n_cand, 1);
+            if (slot < kCandCap) ps.cand[slot] = ((uint32_t)q << 30) | ((uint32_t)y << 15) | (uint32_t)(wi * 32 + bbit);
+            else atomicOr(&ps.kl[q].flags, MPE_F_BLOB_OVERFLOW);
+          }
+        }
+      }
+      __syncwarp();
+      if (ps.n_cand >= kCandCap / 2) process_pooled<kPoolFrames>(a, ps, lane);
+    }
+    __syncwarp();                                              // rowflags / rows are rewritten by the next frame
+  }
+  if (ps.n_cand > 0) process_pooled<kPoolFrames>(a, ps, lane);
+  __syncwarp();
+
+  // ---- order + undistortion over the pooled blobs, one per lane
+  int offs[kPoolFrames + 1];
+  offs[0] = 0;
+#pragma unroll
+  for (int q = 0; q < kPoolFrames; ++q) offs[q + 1] = offs[q] + min(ps.kl[q].n_kept, MPE_MAX_BLOBS);
+  for (int i = lane; i < offs[kPoolFrames]; i += 32) {
+    int q = 0;
+#pragma unroll
+    for (int t = 1; t < kPoolFrames; ++t) q += (i >= offs[t]);
+    emit_blob(a, ps.kl[q], f0 + q, i - offs[q], offs[q + 1] - offs[q]);
+  }
+  if (lane < kPoolFrames) {
+    const int f = f0 + lane;
+    if (f < g.n_frames && !(a.active && !a.active[f])) {
+      a.n_det[f] = offs[lane + 1] - offs[lane];
+      a.flags[f] = ps.kl[lane].flags;
+    }
+  }
+}
+
+template <int kPoolFrames>
+static cudaError_t launch_extract_blobs_pooled(const K1bArgs& a, cudaStream_t st) {
+  static SmemAttrCache configured_pool;
+  int flags_cap = a.g.n_strips * a.g.n_ct;                    // the row flags this launch's geometry can produce
+  if (flags_cap > kMaxFlagWords) flags_cap = kMaxFlagWords;
+  const size_t smem = k1b_pool_stride<kPoolFrames>(flags_cap, a.g.mask_rows) * kPoolWarpsPerCta;
+  cudaError_t e = ensure_dynamic_smem(extract_blobs_pooled_kernel<kPoolFrames>, smem, configured_pool);
+  if (e != cudaSuccess) return e;
+  const int groups = (a.g.n_frames + kPoolFrames - 1) / kPoolFrames;
+  return launch_k(extract_blobs_pooled_kernel<kPoolFrames>, (groups + kPoolWarpsPerCta - 1) / kPoolWarpsPerCta, 32 * kPoolWarpsPerCta, smem, st, a, flags_cap);
+}
+
 cudaError_t launch_extract_blobs(const K1bArgs& a, cudaStream_t st) {
+  // frames per warp: MPE_K1B_POOL = 0 (none) / 2 / 4; default 4 for whole-image batches (the cold pipeline keeps two batches in
+  // flight), none for per-frame ROIs: a tracking step runs alone on its stream, where the shorter chain wins (measured, 8192
+  // streams: 7.38 M frames/s without, 7.36 M with two, 7.11 M with four frames per warp)
+  static int pool_env = -1;
+  if (pool_env < 0) { const char* e = getenv("MPE_K1B_POOL"); pool_env = e ? atoi(e) : -1; if (pool_env < -1) pool_env = -1; }
+  int pool = (pool_env >= 0) ? pool_env : (a.g.rois ? 0 : 4);
+  if (a.g.n_frames < kK1bPoolMinFrames || a.g.max_roi_w > 32767 || a.g.max_roi_h > 32767) pool = 0;
+  if (pool >= 3) return launch_extract_blobs_pooled<4>(a, st);
+  if (pool >= 1) return launch_extract_blobs_pooled<2>(a, st);
   int grid = (a.g.n_frames + kBlobWarpsPerCta - 1) / kBlobWarpsPerCta;
   static SmemAttrCache configured;
   const int flags_cap = a.g.flags_per_frame < kMaxFlagWords ? a.g.flags_per_frame : kMaxFlagWords;
