@@ -836,7 +836,11 @@ cudaError_t launch_p3p_sweep(const K2Args& a, int n_sms, cudaStream_t st) {
     }
     b.group = group;
     const int units = (a.split > 1) ? a.n_frames * a.split : (a.n_frames + group - 1) / group;
-    int g2 = n_sms * MPE_K2_MINBLOCKS;
+    // persistent CTAs: MPE_K2_MINBLOCKS per SM fill the register file (3 x 256 threads x 80 registers), so nothing of another
+    // stream runs beside the sweep; MPE_K2_CTAS_PER_SM = 1 / 2 leaves room (experiments)
+    static int ctas_per_sm = -1;
+    if (ctas_per_sm < 0) { const char* e = getenv("MPE_K2_CTAS_PER_SM"); ctas_per_sm = e ? atoi(e) : 0; }
+    int g2 = n_sms * ((ctas_per_sm >= 1 && ctas_per_sm <= MPE_K2_MINBLOCKS) ? ctas_per_sm : MPE_K2_MINBLOCKS);
     if (mult > 0) g2 *= mult;
     if (g2 > units) g2 = units;
     if (g2 < 1) g2 = 1;
