@@ -79,15 +79,21 @@ class ClockSampler:
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_index, n_gpus=1, enabled=True):
+        """gpu_index: first GPU to watch, n_gpus: how many (one nvidia-smi process for all of them: with one poller per rank,
+        eight of them queried the driver 50 times a second each while the kernels were being launched)."""
+        self.gpus = list(range(gpu_index, gpu_index + n_gpus))
+        self.enabled = enabled
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+            period = "20" if len(self.gpus) == 1 else "50"
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", period,
+                                       "-i", ",".join(str(g) for g in self.gpus)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -99,7 +105,8 @@ class ClockSampler:
             out["error"] = "nvidia-smi not available"
             return out
         self.f.flush()
-        sm, mx, pw, reasons = [], [], [], set()
+        per = {}                                   # GPU index -> (sm samples, max clocks, power samples)
+        reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.f.name) as fh:
             for line in fh.read().splitlines():
@@ -110,19 +117,24 @@ class ClockSampler:
                     ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
                     if ts < t_begin - 0.02 or ts > t_end + 0.02:
                         continue
+                    idx = int(parts[1])
                     sm_v, mx_v = float(parts[2]), float(parts[3])
                     pw_v = float(parts[4])
                 except ValueError:
                     continue
+                sm, mx, pw = per.setdefault(idx, ([], [], []))
                 sm.append(sm_v); mx.append(mx_v); pw.append(pw_v)
                 for n, v in zip(names, parts[6:10]):
                     if v.lower().startswith("active"):
-                        reasons.add(n)
-        if not sm:
+                        reasons.add(n if len(self.gpus) == 1 else f"{n}@gpu{idx}")
+        if not per:
             out["error"] = "no nvidia-smi samples in the window"
         else:
-            out.update({"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "power_w_max": max(pw),
-                        "window_s": round(t_end - t_begin, 3)})
+            med = {i: statistics.median(v[0]) for i, v in per.items()}
+            out.update({"sm_mhz": min(med.values()), "sm_max_mhz": max(max(v[1]) for v in per.values()), "samples": sum(len(v[0]) for v in per.values()),
+                        "power_w_max": max(max(v[2]) for v in per.values()), "window_s": round(t_end - t_begin, 3)})
+            if len(self.gpus) > 1:                 # sm_mhz above is the slowest GPU's median
+                out["per_gpu"] = [{"gpu": i, "sm_mhz": med[i], "power_w_max": max(per[i][2])} for i in sorted(per)]
         out["reasons"] = sorted(reasons)
         return out
 
@@ -435,7 +447,8 @@ def run_tracking(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(1.2)
+    sampler = ClockSampler(0, n_gpus=world, enabled=(local_rank == 0)) if world > 1 else ClockSampler(local_rank)
+    sampler.start(); time.sleep(1.2)
     line = tracking_measure(args, local_rank, args.batch, 512, args.steps, args.warmup, sampler, dist if world > 1 else None, world, rank,
                             cpu=not args.no_cpu, e2e=not args.no_e2e, verify_streams=32 if world > 1 else 0)
     sampler.stop()
@@ -600,25 +613,26 @@ def cold_measure(args, local_rank, world, rank, dist, sampler, B, bps, steps, wa
     rec = C.sizeof(mpe.MpeResult)
     # record gather: the mpe_result records of this rank's batch, all-gathered over NCCL once per batch on a side stream,
     # double buffered, so that the collective of batch i overlaps the kernels of batch i+1 (nothing in the path waits for it).
-    gather = do_gather and world > 1
-    g_in = [torch.zeros((B, rec), dtype=torch.uint8, device=dev) for _ in range(2)] if gather else None
-    g_out = [torch.zeros((world * B, rec), dtype=torch.uint8, device=dev) for _ in range(2)] if gather else None
+    gather = do_gather and world > 1 and not getattr(args, "no_gather", False)
+    n_slots = max(2, int(getattr(args, "gather_slots", 2)))   # ring of gather buffers: a batch waits only for the gather n_slots batches back
+    g_in = [torch.zeros((B, rec), dtype=torch.uint8, device=dev) for _ in range(n_slots)] if gather else None
+    g_out = [torch.zeros((world * B, rec), dtype=torch.uint8, device=dev) for _ in range(n_slots)] if gather else None
     gstream = torch.cuda.Stream(device=dev) if gather else None
-    copied = [torch.cuda.Event() for _ in range(2)]
-    gathered = [torch.cuda.Event() for _ in range(2)]
-    g_t0 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    g_t1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(n_slots)]
+    gathered = [torch.cuda.Event() for _ in range(n_slots)]
+    g_t0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_slots)]
+    g_t1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_slots)]
     batch_no = [0]
     gather_on = [gather]
 
     def batch_device(single=False):
         k = 0 if single else batch_no[0] % n_ctx       # which context / stream takes this batch
         cx, sx = ctxs[k], streams[k]
-        i = batch_no[0] & 1
+        i = batch_no[0] % n_slots
         batch_no[0] += 1
         cx.estimate_batch_device_async(dev_frames.data_ptr(), W, W * H, W, H, B)
         if gather_on[0]:
-            if batch_no[0] > 2:
+            if batch_no[0] > n_slots:
                 sx.wait_event(gathered[i])                # the gather that last read this buffer has finished
             cx.copy_results_device(g_in[i].data_ptr(), B)
             copied[i].record(sx)
@@ -672,22 +686,25 @@ def cold_measure(args, local_rank, world, rank, dist, sampler, B, bps, steps, wa
     e0.record(stream)
     for sx in streams[1:]:
         sx.wait_event(e0)                                 # the other stream starts inside the timed region too
+    th0 = time.perf_counter()
     for _ in range(steps):
         for _b in range(bps):
             batch_device()
+    th1 = time.perf_counter()                             # host time to enqueue the timed batches (launches are asynchronous)
     join()                                                # the timed region ends when every batch and the last record gather have landed
     e1.record(stream)
     barrier()
     t_load1 = time.time()
     ms_total = e0.elapsed_time(e1)
+    host_enqueue_ms_per_batch = (th1 - th0) * 1e3 / (steps * bps)
     launches_timed = sum(c.launch_count() for c in ctxs) - launches1
     gather_info = None
     if gather:
-        gms = float(np.mean([g_t0[i].elapsed_time(g_t1[i]) for i in range(2)]))
-        oks = [sharding.verify_gather(g_out[i], g_in[i], rank, world, dist) for i in range(2)]
+        gms = float(np.mean([g_t0[i].elapsed_time(g_t1[i]) for i in range(n_slots)]))
+        oks = [sharding.verify_gather(g_out[i], g_in[i], rank, world, dist) for i in range(n_slots)]
         okt = torch.tensor([1 if all(oks) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        gather_info = {"collective": "all_gather_into_tensor of the batch's mpe_result records (NCCL), side stream, double buffered, once per batch",
+        gather_info = {"collective": "all_gather_into_tensor of the batch's mpe_result records (NCCL), side stream, ring of %d buffers, once per batch" % n_slots,
                        "bytes_per_rank_per_batch": B * rec, "ms_per_gather_rank0": gms, "verified_all_ranks": bool(okt.item()),
                        "verification": "own block byte for byte + checksum exchange for the other ranks' blocks (sharding.verify_gather), both buffers, after the timed region"}
     # per-kernel durations: a separate pass on ONE context with CUDA events around every stage, the record gather switched off
@@ -702,7 +719,11 @@ def cold_measure(args, local_rank, world, rank, dist, sampler, B, bps, steps, wa
     fp64_peak = ctx.probe_fp64_peak() if rank == 0 else None
     clocks = sampler.window(t_load0, t_load1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    ms_step_per_rank = None
     if world > 1:
+        allt = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        ms_step_per_rank = [float(x) / steps for x in allt.tolist()]   # the job's time is the slowest rank's
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / steps
@@ -743,7 +764,7 @@ def cold_measure(args, local_rank, world, rank, dist, sampler, B, bps, steps, wa
                "clocks": sampler.window(tw0, tw1),
                "api": "mpe_estimate_batch (pinned host frames -> host mpe_result records)"}
         assert int(results_to_arrays(r)["updated"].sum()) == n_updated
-    out = dict(scene=scene, kt=kt, value=value, ms_step=ms_step, clocks=clocks, e2e=e2e, launches=launches_timed, n_ctx=n_ctx, n_updated=n_updated,
+    out = dict(scene=scene, kt=kt, value=value, ms_step=ms_step, clocks=clocks, e2e=e2e, launches=launches_timed, host_enqueue_ms_per_batch=host_enqueue_ms_per_batch, ms_step_per_rank=ms_step_per_rank, n_ctx=n_ctx, n_updated=n_updated,
                gather=gather_info, oracle_check=oracle_check, fp64_peak=fp64_peak, window=(t_load0, t_load1))
     if do_cpu and rank == 0:
         fps, n, dt = cpu_single_thread(scene, max_seconds=cpu_seconds)
@@ -800,7 +821,8 @@ def run_cold(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    sampler = ClockSampler(local_rank)
+    # one poller per node (local rank 0 watches every GPU of the job); the other ranks do not touch nvidia-smi
+    sampler = ClockSampler(0, n_gpus=max(world, 1), enabled=(local_rank == 0)) if world > 1 else ClockSampler(local_rank)
     sampler.start()                      # started early: nvidia-smi needs ~1 s before its first sample
     W, H, B, bps = args.width, args.height, args.batch, args.batches_per_step
     m = cold_measure(args, local_rank, world, rank, dist if world > 1 else None, sampler, B, bps, args.steps, args.warmup, args.leds, W, H, args.seed,
@@ -816,13 +838,15 @@ def run_cold(args):
             "data": "synthetic",
             "config": make_config(args),
             "parallelism": f"frames sharded over {world} GPU(s), NCCL all-gather of the result records per batch" if world > 1 else "1 GPU",
-            "batches_in_flight": m["n_ctx"], "frames_with_pose_per_batch": m["n_updated"], "oracle_check": m["oracle_check"],
+            "batches_in_flight": m["n_ctx"], "contour_frames_per_warp": int(os.environ.get("MPE_K1B_POOL", "4")) or 1, "frames_with_pose_per_batch": m["n_updated"], "oracle_check": m["oracle_check"],
             "parity_note": "the CPU oracle these results are checked against is pinned to the UNMODIFIED reference sources built in oracle/_ref (stand-in Eigen): "
                            "discrete outputs and Gauss-Newton iteration counts equal; what no build here can pin is real Eigen's last-ulp rounding, and the "
                            "exit test of optimisePose (1e-13) sits at that floor, so +-1 iteration against a real-Eigen binary cannot be excluded",
             "clocks": m["clocks"],
             "e2e": m["e2e"],
             "gpu_launches": m["launches"],
+            "host_enqueue_ms_per_batch": m["host_enqueue_ms_per_batch"],
+            "ms_per_step_per_rank": m["ms_step_per_rank"],
             "gather": m["gather"],
             "roofline": {"kernel": "scan_kernel (K1a: TMA-streamed threshold scan of every ROI byte; findLeds hot loop)", "bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                          "frac": k1_gbs / peak, "peak_source": peak_src, "traffic": load_traffic(B, W, H),
@@ -871,6 +895,12 @@ def run_cold(args):
 
 
 def main():
+    # Several ranks: the record gather (an NCCL kernel) shares each GPU with the pipeline.  The four-frames-per-warp contour kernel
+    # (long-running CTAs on every SM) then keeps NCCL's CTAs waiting and the collective resident for ~0.5 ms per batch instead of
+    # 0.05 ms: measured on 2 x B200 10.63 M frames/s with it, 11.01 M without.  Alone on the GPU it is the faster choice (5.85 M
+    # against 5.59 M frames/s).  The library reads the knob once, at its first contour launch.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("MPE_K1B_POOL", "0")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -889,6 +919,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the other configurations (tracking, latency, 1080p, 8 LEDs)")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the CPUs next to its GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the NCCL gather of the records out (diagnostic)")
+    ap.add_argument("--gather-slots", type=int, default=2, help="N > 1: depth of the ring of gather buffers")
     ap.add_argument("--contexts", type=int, default=2, help="batches in flight in the device-resident measurement (one context + stream each)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

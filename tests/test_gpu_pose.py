@@ -228,6 +228,36 @@ def test_sweep_reject_filter_never_changes_a_vote(gpu_ctx_752):
     assert n_cases >= 70 and n_votes > 1000
 
 
+def test_pooled_contour_kernel_matches_per_frame_kernel():
+    """From 2048 whole-image frames on, K1b serves four frames per warp (extract_blobs_pooled_kernel: pooled border following);
+    below that a warp per frame.  2067 frames (not a multiple of 4 or 16: ragged last group and last CTA) in a shuffled order, some of
+    them empty and some with extra blobs, against the same frames run in chunks of 500: every record identical byte for byte."""
+    import rpg_monocular_pose_estimator_b200 as mpe
+    from rpg_monocular_pose_estimator_b200.pose_estimator import results_to_arrays
+    from tests.helpers import random_blob_image
+    n_distinct, n_total = 96, 2067
+    sc = synth.make_cold_scene(n_distinct, n_leds=5, seed=9100)
+    rng = np.random.default_rng(77)
+    distinct = sc.frames.copy()
+    distinct[5] = 0                                                           # nothing to find
+    distinct[6] = 255                                                         # one blob as large as the image (rejected by the area filter)
+    for f in (7, 8, 9):                                                       # many blobs: more candidates than LEDs
+        distinct[f] = random_blob_image(rng, sc.height, sc.width, n_blobs=30, kind="mixed")
+    order = rng.integers(0, n_distinct, n_total)
+    frames = np.ascontiguousarray(distinct[order])
+    ctx = mpe.Context(0, n_total, sc.width, sc.height)
+    try:
+        _config(ctx, sc)
+        big = results_to_arrays(ctx.estimate_batch(frames)).copy()
+        parts = [results_to_arrays(ctx.estimate_batch(frames[i:i + 500])).copy() for i in range(0, n_total, 500)]
+    finally:
+        ctx.close()
+    small = np.concatenate(parts)
+    assert big["n_det"].max() > 5 and (big["n_det"] == 0).any()
+    for f in range(n_total):
+        assert big[f].tobytes() == small[f].tobytes(), (f, int(order[f]), int(big[f]["n_det"]), int(small[f]["n_det"]))
+
+
 def test_large_batch_kernels_match_oracle():
     """Batches above 1024 frames take the throughput kernels (thread per subset / thread per frame, CTA per frame in the sweep),
     smaller ones the lane-cooperative kernels; both must give the oracle's results.  64 distinct frames replicated to 1280:
