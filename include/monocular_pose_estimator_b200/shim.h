@@ -36,8 +36,13 @@
 #include <Eigen/Dense>
 #if __has_include(<opencv2/core.hpp>)
 #include <opencv2/core.hpp>
+#if __has_include(<opencv2/imgproc.hpp>) && __has_include(<opencv2/calib3d.hpp>) && !defined(MPE_SHIM_NO_OPENCV_DRAWING)
+#include <opencv2/calib3d.hpp>
+#include <opencv2/imgproc.hpp>
+#define MPE_SHIM_OPENCV_DRAWING 1      // augmentImage draws the reference's overlay (visualization.cpp) with OpenCV, on the host
+#endif
 #else
-#include <opencv2/opencv.hpp>
+#include <opencv2/opencv.hpp>           // one-header installations: define MPE_SHIM_OPENCV_DRAWING if projectPoints / line / circle / rectangle exist
 #endif
 namespace monocular_pose_estimator {
 // datatypes.h:38-52 (all of them, so that sources written against the reference's header compile unchanged) + led_detector.h:39
@@ -138,6 +143,33 @@ namespace detail {
 inline void check(mpe_ctx* c, int rc, const char* what) {
   if (rc != MPE_OK) throw std::runtime_error(std::string(what) + ": " + (c ? mpe_last_error(c) : "no context"));
 }
+#ifdef MPE_SHIM_OPENCV_DRAWING
+// Visualization::createVisualizationImage (visualization.cpp:57-104) + projectOrientationVectorsOnImage (:37-55): body axes in
+// red / green / blue from the projected trivector, a circle per detection centre, the region of interest.  `pose` row-major 4x4.
+inline void draw_overlay(ImageT& image, const double pose[16], const CameraMatT& K, const std::vector<double>& D, const RectT& roi,
+                         const std::vector<Point2fT>& centers) {
+  const double len = 0.075;                                       // orientation_vector_length
+  const double O[4][4] = {{0, len, 0, 0}, {0, 0, len, 0}, {0, 0, 0, len}, {1, 1, 1, 1}};   // columns: origin, x, y, z axis tips
+  std::vector<cv::Point3f> pts(4);
+  for (int c = 0; c < 4; ++c) {
+    double v[3];
+    for (int r = 0; r < 3; ++r) {                                 // transform * orientation_vector_points, k ascending
+      double acc = pose[4 * r] * O[0][c];
+      for (int k = 1; k < 4; ++k) acc = acc + pose[4 * r + k] * O[k][c];
+      v[r] = acc;
+    }
+    pts[c] = cv::Point3f((float)v[0], (float)v[1], (float)v[2]);
+  }
+  std::vector<cv::Point2f> proj;
+  cv::Mat rvec = cv::Mat::zeros(3, 1, CV_64F), tvec = cv::Mat::zeros(3, 1, CV_64F);
+  cv::projectPoints(pts, rvec, tvec, K, D, proj);
+  cv::line(image, proj[0], proj[1], CV_RGB(255, 0, 0), 2);
+  cv::line(image, proj[0], proj[2], CV_RGB(0, 255, 0), 2);
+  cv::line(image, proj[0], proj[3], CV_RGB(0, 0, 255), 2);
+  for (size_t i = 0; i < centers.size(); ++i) cv::circle(image, centers[i], 10, CV_RGB(255, 0, 0), 2);
+  cv::rectangle(image, roi, CV_RGB(0, 0, 255), 2);
+}
+#endif
 inline void camera_to_rowmajor(const CameraMatT& K, double out[9]) {
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[3 * r + c] = cam_at(K, r, c);
 }
@@ -227,8 +259,17 @@ class PoseEstimator {
     markers_dirty_ = true;
   }
   List4DPoints getMarkerPositions() { return object_points_; }
-  // pose_estimator.cpp:44-48 forwards to Visualization::createVisualizationImage (debug overlay, out of scope): the image is left as is
+  // pose_estimator.cpp:44-48 -> Visualization::createVisualizationImage (visualization.cpp:57-104): the debug overlay MPENode
+  // publishes when somebody subscribes (monocular_pose_estimator.cpp:198-214).  Host side, OpenCV drawing, like the reference —
+  // it is next to the pose path, not part of it; what it draws (pose, region of interest, detection centres) came back from the
+  // device in the result record.  Without OpenCV's drawing API (stand-in types) the image is left as it is.
+#ifdef MPE_SHIM_OPENCV_DRAWING
+  void augmentImage(ImageT& image) {
+    detail::draw_overlay(image, predicted_pose_, camera_matrix_K_, camera_distortion_coeffs_, region_of_interest_, distorted_detection_centers_);
+  }
+#else
   void augmentImage(ImageT& /*image*/) {}
+#endif
   void setPredictedPose(const Matrix4dT& pose, double time) { fromEigen(pose, predicted_pose_); predicted_time_ = time; }
   Matrix4dT getPredictedPose() { return toEigen(predicted_pose_); }
   Matrix6d getPoseCovariance() { Matrix6d c; for (int r = 0; r < 6; ++r) for (int q = 0; q < 6; ++q) c(r, q) = cov_[6 * r + q]; return c; }

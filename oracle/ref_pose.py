@@ -36,6 +36,8 @@ class _Callbacks(C.Structure):
         ("bounding_rect", C.CFUNCTYPE(None, ip, C.c_int, ip)),
         ("moments", C.CFUNCTYPE(None, ip, C.c_int, dp)),
         ("undistort_points", C.CFUNCTYPE(None, fp, C.c_int, dp, dp, C.c_int, dp, fp)),
+        ("project_points", C.CFUNCTYPE(None, fp, C.c_int, dp, dp, dp, dp, C.c_int, fp)),
+        ("draw", C.CFUNCTYPE(None, ucp, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, ip, dp, C.c_int)),
     ]
 
 
@@ -90,11 +92,32 @@ def _make_callbacks():
         out = cv2.undistortPoints(s, Km, Dv, None, Pm)
         np.ctypeslib.as_array(dst, shape=(n, 2))[:] = out.reshape(n, 2)
 
+    def project_points(xyz, n, rvec, tvec, K, D, nD, out):
+        pts = np.ctypeslib.as_array(xyz, shape=(n, 3)).astype(np.float32).reshape(n, 1, 3)
+        r = np.ctypeslib.as_array(rvec, shape=(3,)).copy().reshape(3, 1)
+        t = np.ctypeslib.as_array(tvec, shape=(3,)).copy().reshape(3, 1)
+        Km = np.ctypeslib.as_array(K, shape=(3, 3)).copy()
+        Dv = np.ctypeslib.as_array(D, shape=(nD,)).copy() if nD > 0 else np.zeros(0)
+        img_pts, _ = cv2.projectPoints(pts, r, t, Km, Dv)
+        np.ctypeslib.as_array(out, shape=(n, 2))[:] = img_pts.reshape(n, 2).astype(np.float32)   # std::vector<cv::Point2f>
+
+    def draw(img, rows, cols, step, channels, what, geom, color, thickness):
+        buf = np.ctypeslib.as_array(img, shape=(rows * step,))
+        view = np.lib.stride_tricks.as_strided(buf, shape=(rows, cols, channels), strides=(step, channels, 1))
+        col = tuple(float(color[i]) for i in range(4))
+        g = [int(geom[i]) for i in range(4)]
+        if what == 0:
+            cv2.line(view, (g[0], g[1]), (g[2], g[3]), col, thickness)
+        elif what == 1:
+            cv2.circle(view, (g[0], g[1]), g[2], col, thickness)
+        else:
+            cv2.rectangle(view, (g[0], g[1], g[2], g[3]), col, thickness)
+
     cb = _Callbacks()
     fields = dict(_Callbacks._fields_)
     for name, fn in [("threshold", threshold), ("gaussian_blur", gaussian_blur), ("find_contours", find_contours),
                      ("contour_area", contour_area), ("bounding_rect", bounding_rect), ("moments", moments),
-                     ("undistort_points", undistort_points)]:
+                     ("undistort_points", undistort_points), ("project_points", project_points), ("draw", draw)]:
         setattr(cb, name, fields[name](fn))
     return cb, state
 
@@ -141,6 +164,7 @@ def lib():
             ("mper_estimate_body_pose", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_double], C.c_int),
             ("mper_get_roi", [C.c_void_p, ip], None),
             ("mper_get_distorted_centers", [C.c_void_p, fp], C.c_int),
+            ("mper_create_visualization_image", [C.c_void_p, C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_int, ip, fp, C.c_int], None),
         ]:
             fn = getattr(L, name)
             fn.argtypes = args
@@ -231,6 +255,20 @@ def find_leds(image, roi, threshold_value, gaussian_sigma, min_blob_area, max_bl
                              C.byref(n_px), centers.ctypes.data_as(fp))
     out_px = px[: n_px.value].copy() if (n > 0 or pixel_positions is not None) else None
     return out_px, centers[:n].copy()
+
+
+def create_visualization_image(image_bgr, pose, K, D, roi, centers):
+    """Visualization::createVisualizationImage of the reference build (visualization.cpp:57-104) on a copy of a 3-channel image:
+    its projectPoints / line / circle / rectangle calls reach the cv2 functions of the same name."""
+    img = np.ascontiguousarray(image_bgr, np.uint8).copy()
+    assert img.ndim == 3 and img.shape[2] == 3
+    pose = np.ascontiguousarray(pose, np.float64).reshape(16); K = np.ascontiguousarray(K, np.float64).reshape(9)
+    D = np.ascontiguousarray(D, np.float64)
+    c = np.ascontiguousarray(centers, np.float32).reshape(-1, 2)
+    r = (C.c_int * 4)(*[int(v) for v in roi])
+    lib().mper_create_visualization_image(img.ctypes.data_as(C.c_void_p), img.shape[0], img.shape[1], img.strides[0], _dpp(pose), _dpp(K),
+                                          _dpp(D), len(D), r, c.ctypes.data_as(fp), len(c))
+    return img
 
 
 class PoseEstimatorRef(pose_oracle.PoseEstimatorOracle):

@@ -24,16 +24,6 @@
 
 using namespace monocular_pose_estimator;
 
-// ---- link-time stand-ins for what is out of scope ------------------------------------------------------------------
-// visualization.cpp needs ros/ros.h and OpenCV drawing; PoseEstimator::augmentImage (pose_estimator.cpp:44-48) is its only
-// caller and is not on the pose path.
-namespace monocular_pose_estimator {
-void Visualization::createVisualizationImage(cv::Mat&, Eigen::Matrix4d, const cv::Mat, const std::vector<double>, cv::Rect,
-                                             std::vector<cv::Point2f>) {}
-void Visualization::projectOrientationVectorsOnImage(cv::Mat&, const std::vector<cv::Point3f>, const cv::Mat,
-                                                     const std::vector<double>) {}
-}  // namespace monocular_pose_estimator
-
 // ---- OpenCV entry points forwarded to the registered callbacks -----------------------------------------------------
 namespace cv_shim {
 cv_shim_callbacks& callbacks() { static cv_shim_callbacks c = {}; return c; }
@@ -87,6 +77,24 @@ void undistortPoints(const std::vector<Point2f>& src, std::vector<Point2f>& dst,
   dst.resize(src.size());
   for (size_t i = 0; i < src.size(); ++i) dst[i] = Point2f(out[2 * i], out[2 * i + 1]);
 }
+void projectPoints(const std::vector<Point3f>& pts, const Mat& rvec, const Mat& tvec, const Mat& K, const std::vector<double>& D,
+                   std::vector<Point2f>& out) {
+  double k[9], r[3], t[3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) k[3 * i + j] = K.at<double>(i, j);
+  for (int i = 0; i < 3; ++i) { r[i] = rvec.at<double>(i, 0); t[i] = tvec.at<double>(i, 0); }
+  std::vector<float> in(3 * pts.size()), o(2 * pts.size());
+  for (size_t i = 0; i < pts.size(); ++i) { in[3 * i] = pts[i].x; in[3 * i + 1] = pts[i].y; in[3 * i + 2] = pts[i].z; }
+  cv_shim::callbacks().project_points(in.data(), (int)pts.size(), r, t, k, D.data(), (int)D.size(), o.data());
+  out.resize(pts.size());
+  for (size_t i = 0; i < pts.size(); ++i) out[i] = Point2f(o[2 * i], o[2 * i + 1]);
+}
+static void draw(Mat& img, int what, int a, int b, int c, int d, const Scalar& color, int thickness) {
+  const int g[4] = {a, b, c, d};
+  cv_shim::callbacks().draw(img.data, img.rows, img.cols, (long)img.step, img.channels(), what, g, color.val, thickness);
+}
+void line(Mat& img, Point p1, Point p2, const Scalar& color, int thickness) { draw(img, 0, p1.x, p1.y, p2.x, p2.y, color, thickness); }
+void circle(Mat& img, Point c, int radius, const Scalar& color, int thickness) { draw(img, 1, c.x, c.y, radius, 0, color, thickness); }
+void rectangle(Mat& img, Rect r, const Scalar& color, int thickness) { draw(img, 2, r.x, r.y, r.width, r.height, color, thickness); }
 }  // namespace cv
 
 namespace {
@@ -115,6 +123,18 @@ List2DPoints list2(const double* p, int n) { List2DPoints l(n); for (int i = 0; 
 extern "C" {
 
 void mper_set_cv_callbacks(const cv_shim_callbacks* c) { cv_shim::callbacks() = *c; }
+
+// Visualization::createVisualizationImage (visualization.cpp:57-104) on a 3-channel 8-bit image, in place
+void mper_create_visualization_image(unsigned char* img, int rows, int cols, long step, const double pose[16], const double K[9],
+                                     const double* D, int nD, const int roi_xywh[4], const float* centers, int n_centers) {
+  cv::Mat image(rows, cols, CV_8UC3, img, (size_t)step);
+  cv::Mat Km(3, 3, CV_64F);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Km.at<double>(i, j) = K[3 * i + j];
+  std::vector<double> Dv(D, D + nD);
+  std::vector<cv::Point2f> c((size_t)n_centers);
+  for (int i = 0; i < n_centers; ++i) c[(size_t)i] = cv::Point2f(centers[2 * i], centers[2 * i + 1]);
+  Visualization::createVisualizationImage(image, m4_from_rowmajor(pose), Km, Dv, cv::Rect(roi_xywh[0], roi_xywh[1], roi_xywh[2], roi_xywh[3]), c);
+}
 
 int mper_p3p(const double f[9], const double P[9], double sol[48]) {
   Eigen::Matrix3d fv, wp;

@@ -9,3 +9,4 @@ from .synth import Params  # noqa: F401
 from ._lib import load_library, MpeError, MpeResult, MPE_MAX_LEDS, MPE_MAX_DET, MPE_MAX_BLOBS  # noqa: F401
 from .led_detector import LEDDetector  # noqa: F401
 from .pose_estimator import PoseEstimator, Context  # noqa: F401
+from .visualization import Visualization  # noqa: F401

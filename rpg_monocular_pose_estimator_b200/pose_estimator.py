@@ -488,6 +488,13 @@ class PoseEstimator:
         self.last_flags = flags
         return px
 
+    def augmentImage(self, image):
+        """pose_estimator.cpp:44-48: draws the body axes, the detections and the region of interest into a 3-channel image (host
+        side, OpenCV drawing — as in the reference this is debug output next to the pose path, not part of it)."""
+        from .visualization import Visualization
+        return Visualization.createVisualizationImage(image, self.predicted_pose_, self.camera_matrix_K_, self.camera_distortion_coeffs_,
+                                                      self.region_of_interest_, self.distorted_detection_centers_)
+
     def estimateBodyPose(self, image, time_to_predict):
         """pose_estimator.cpp:62-147"""
         self.pose_updated_ = False

@@ -89,3 +89,24 @@ def test_predict_pose_project_markers_determine_roi_bit_identical():
             assert tuple(r) == roi, (i, tuple(r), roi)
     # degenerate predictions far to the right of the image: the clamped extent is < 1 -> whole image (led_detector.cpp:166-169)
     assert LEDDetector.determineROI(np.full((5, 2), 5000.0), (752, 480), 20, K, D) == (0, 0, 752, 480)
+
+
+def test_pose_estimator_augment_image_draws_the_last_result():
+    """PoseEstimator.augmentImage (pose_estimator.cpp:44-48) only touches host state: checked here without a device by handing the
+    mirror a placeholder context."""
+    from rpg_monocular_pose_estimator_b200.pose_estimator import PoseEstimator
+    from rpg_monocular_pose_estimator_b200.visualization import Visualization
+    from rpg_monocular_pose_estimator_b200 import synth
+    K, D = synth.camera(752, 480)
+    est = PoseEstimator(context=object())
+    est.camera_matrix_K_, est.camera_distortion_coeffs_ = K, D
+    est.predicted_pose_ = np.eye(4); est.predicted_pose_[:3, 3] = [0.03, -0.02, 0.7]
+    est.region_of_interest_ = (200, 150, 180, 120)
+    est.distorted_detection_centers_ = np.array([[250.5, 200.25], [300.0, 210.0]], np.float32)
+    img = np.zeros((480, 752, 3), np.uint8)
+    out = est.augmentImage(img)
+    assert out is img and img.any()
+    want = Visualization.createVisualizationImage(np.zeros((480, 752, 3), np.uint8), est.predicted_pose_, K, D, est.region_of_interest_,
+                                                  est.distorted_detection_centers_)
+    assert np.array_equal(img, want)
+    assert (img[150, 200:380] == (255, 0, 0)).all()            # the ROI rectangle is blue in BGR

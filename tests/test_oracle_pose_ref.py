@@ -378,3 +378,65 @@ def make_jump(sc, f):
     T = synth.sample_pose(rng, sc.K, sc.D, sc.markers, sc.width, sc.height, z_range=(0.6, 0.9), margin=120.0)
     dist, _, _ = synth.project_distorted(sc.K, sc.D, T, sc.markers)
     return synth.render_frame(rng, sc.width, sc.height, dist)
+
+
+# ---- visualisation: the reference's own visualization.cpp against the product's host mirrors ----------
+def _overlay_cases(n, seed=4242):
+    from scipy.spatial.transform import Rotation
+    K, D = synth.camera(752, 480)
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        img = np.repeat(rng.integers(0, 255, (480, 752, 1), dtype=np.uint8), 3, axis=2)     # cvtColor(GRAY2RGB) of a camera image
+        T = np.eye(4)
+        T[:3, :3] = Rotation.random(random_state=seed + i).as_matrix()
+        T[:3, 3] = [rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3), rng.uniform(0.25, 1.5)]   # incl. axes that leave the image
+        roi = (int(rng.integers(0, 700)), int(rng.integers(0, 440)), int(rng.integers(1, 400)), int(rng.integers(1, 300)))
+        centers = rng.uniform(-30, 800, (int(rng.integers(0, 9)), 2)).astype(np.float32)      # x.5 roundings, off-image centres
+        if i % 7 == 0 and len(centers):
+            centers[0] = np.floor(centers[0]) + 0.5                                            # round-half-to-even of cv::Point(Point2f)
+        yield img, T, K, D, roi, centers
+
+
+def test_visualization_mirror_equals_reference_source():
+    """Visualization::createVisualizationImage compiled from the reference's visualization.cpp (projectPoints / line / circle /
+    rectangle reach cv2) against rpg_monocular_pose_estimator_b200.visualization (what PoseEstimator.augmentImage calls): identical
+    images."""
+    from rpg_monocular_pose_estimator_b200.visualization import Visualization
+    n = 0
+    for img, T, K, D, roi, centers in _overlay_cases(150):
+        want = ref_pose.create_visualization_image(img, T, K, D, roi, centers)
+        got = Visualization.createVisualizationImage(img.copy(), T, K, D, roi, centers)
+        assert not np.array_equal(want, img)
+        assert np.array_equal(want, got), n
+        n += 1
+
+
+def test_cpp_shim_overlay_equals_reference_source():
+    """The C++ shim's augmentImage code (detail::draw_overlay, real-types mode with the drawing API on) compiled against the same
+    stand-ins as the reference source: identical images."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_pose.lib()                                                  # builds / loads libref_pose.so and registers the cv2 callbacks
+    so = os.path.join(root, "build", "libshim_overlay.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + os.path.join(root, "include"),
+                           "-I" + os.path.join(root, "oracle", "eigen_shim"), "-I" + os.path.join(root, "oracle", "cv_shim"),
+                           os.path.join(root, "tests", "cpp", "shim_overlay_capi.cpp"), "-o", so,
+                           "-L" + os.path.join(root, "rpg_monocular_pose_estimator_b200"), "-lmpe_b200",
+                           "-L" + os.path.join(root, "oracle", "_ref"), "-lref_pose",
+                           "-Wl,-rpath," + os.path.join(root, "rpg_monocular_pose_estimator_b200"), "-Wl,-rpath," + os.path.join(root, "oracle", "_ref")])
+    L = C.CDLL(so)
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.shim_draw_overlay.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_int, ip, fp, C.c_int]
+    L.shim_draw_overlay.restype = None
+    for n, (img, T, K, D, roi, centers) in enumerate(_overlay_cases(60, seed=777)):
+        want = ref_pose.create_visualization_image(img, T, K, D, roi, centers)
+        got = np.ascontiguousarray(img).copy()
+        pose = np.ascontiguousarray(T, np.float64).reshape(16); Kf = np.ascontiguousarray(K, np.float64).reshape(9)
+        Dv = np.ascontiguousarray(D, np.float64); c = np.ascontiguousarray(centers, np.float32).reshape(-1, 2)
+        r = (C.c_int * 4)(*roi)
+        L.shim_draw_overlay(got.ctypes.data_as(C.c_void_p), got.shape[0], got.shape[1], got.strides[0], pose.ctypes.data_as(dp),
+                            Kf.ctypes.data_as(dp), Dv.ctypes.data_as(dp), len(Dv), r, c.ctypes.data_as(fp), len(c))
+        assert np.array_equal(want, got), n
