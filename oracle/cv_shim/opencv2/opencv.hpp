@@ -20,6 +20,8 @@
 #define CV_8UC3 16
 #define CV_64FC1 6
 #define CV_RGB(r, g, b) cv::Scalar((b), (g), (r), 0)
+#define CV_GRAY2RGB 8
+#define CV_GRAY2BGR 8
 #define CV_RETR_EXTERNAL 0
 #define CV_CHAIN_APPROX_NONE 1
 
@@ -93,6 +95,19 @@ class Mat {
  private:
   std::shared_ptr<std::vector<uchar> > owner_;
 };
+
+// cv::cvtColor for the one conversion the ROS node makes (GRAY2RGB, monocular_pose_estimator.cpp:201; in place allowed)
+inline void cvtColor(const Mat& src, Mat& dst, int code) {
+  if (code != CV_GRAY2RGB || src.type() != CV_8UC1) return;
+  Mat out(src.rows, src.cols, CV_8UC3);
+  for (int r = 0; r < src.rows; ++r)
+    for (int c = 0; c < src.cols; ++c) {
+      const uchar v = src.data[(size_t)r * src.step + (size_t)c];
+      uchar* o = out.data + (size_t)r * out.step + (size_t)3 * c;
+      o[0] = v; o[1] = v; o[2] = v;
+    }
+  dst = out;
+}
 
 struct NoArray {};
 inline NoArray noArray() { return NoArray(); }
