@@ -3,7 +3,8 @@
 // resolves to tests/ros_stub/monocular_pose_estimator_lib/pose_estimator.h -> include/monocular_pose_estimator_b200/shim.h, and
 // ROS / cv_bridge / dynamic_reconfigure are the in-process stand-ins of tests/ros_stub (Eigen / OpenCV: the stand-ins of oracle/).
 // The harness plays roscore: marker list on the parameter server, one CameraInfo, a reconfigure call, then one sensor_msgs/Image
-// per frame of a scene file (same format as tests/cpp/shim_real_types_demo.cpp), and prints what the node published.
+// per frame of a scene file (same format as tests/cpp/shim_real_types_demo.cpp), and prints what the node published.  With the
+// argument `nodelet` the node is created the way the nodelet manager does it (the reference's nodelet.cpp, also unmodified).
 //   per frame:  index  published(0/1)  roi x y w h  gauss-newton iterations  pose 4x4 row-major  |  position xyz  orientation xyzw  cov[0]
 // everything the node header includes, first (all guarded), so that the access trick below touches the MPENode class only
 #include <sstream>
@@ -20,9 +21,15 @@
 #include <dynamic_reconfigure/server.h>
 #include <monocular_pose_estimator/MonocularPoseEstimatorConfig.h>
 #include "monocular_pose_estimator_lib/pose_estimator.h"
+#include <nodelet/nodelet.h>
 #define private public            // the harness reads MPENode::trackable_object_ (ROI, iteration count); the node's own TU is untouched
+#define protected public          // ... and MPENodelet::mpe_node
 #include "monocular_pose_estimator/monocular_pose_estimator.h"
+#include "monocular_pose_estimator/nodelet.h"
+#undef protected
 #undef private
+
+extern "C" nodelet::Nodelet* ros_stub_create_plugin();   // what PLUGINLIB_EXPORT_CLASS in the reference's nodelet.cpp expands to here
 
 #include <cstdio>
 #include <cstring>
@@ -30,7 +37,8 @@
 using namespace monocular_pose_estimator;
 
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: mpenode_on_shim scene.bin\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: mpenode_on_shim scene.bin [nodelet]\n"); return 2; }
+  const bool as_nodelet = argc > 2 && std::strcmp(argv[2], "nodelet") == 0;   // load the node the way the nodelet manager does
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror("open"); return 2; }
   int hdr[4];
@@ -56,7 +64,18 @@ int main(int argc, char** argv) {
     bus.sinks["estimated_pose"] = [&](const void* m) { last_pose = *static_cast<const geometry_msgs::PoseWithCovarianceStamped*>(m); got_pose = true; };
     bus.sinks["image_with_detections"] = [&](const void* m) { overlay_bytes = static_cast<const sensor_msgs::Image*>(m)->data.size(); };
 
-    MPENode node((ros::NodeHandle()), ros::NodeHandle("~"));
+    std::unique_ptr<MPENode> direct;
+    std::unique_ptr<nodelet::Nodelet> plugin;
+    MPENode* node_ptr = nullptr;
+    if (as_nodelet) {
+      plugin.reset(ros_stub_create_plugin());                       // PLUGINLIB_EXPORT_CLASS(monocular_pose_estimator::MPENodelet, nodelet::Nodelet)
+      plugin->init();                                               // MPENodelet::onInit (nodelet.cpp:24-28)
+      node_ptr = static_cast<MPENodelet*>(plugin.get())->mpe_node.get();
+    } else {
+      direct.reset(new MPENode((ros::NodeHandle()), ros::NodeHandle("~")));   // node.cpp:27
+      node_ptr = direct.get();
+    }
+    MPENode& node = *node_ptr;
     if (bus.shutdown_requested) { fprintf(stderr, "node asked for shutdown\n"); return 1; }
 
     MonocularPoseEstimatorConfig cfg;                               // dynamic_reconfigure pushes the launch file's values

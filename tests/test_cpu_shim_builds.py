@@ -24,7 +24,7 @@ def test_shim_demos_compile_and_link():
 
 
 def test_unmodified_ros_node_compiles_and_links_against_the_shim(tmp_path):
-    """monocular_pose_estimator/src/monocular_pose_estimator.cpp (MPENode: constructor, cameraInfoCallback,
+    """monocular_pose_estimator/src/{monocular_pose_estimator,nodelet,node}.cpp (MPENode: constructor, cameraInfoCallback,
     imageCallback incl. the PoseWithCovarianceStamped packing and the overlay branch, dynamicParametersCallback) is compiled UNMODIFIED
     from /root/reference; its `#include "monocular_pose_estimator_lib/pose_estimator.h"` resolves to the shim.  ROS, cv_bridge and
     dynamic_reconfigure are in-process stand-ins (tests/ros_stub).  Running it needs a GPU; here: it links, and without a device the
@@ -52,8 +52,11 @@ def test_unmodified_ros_node_compiles_and_links_against_the_shim(tmp_path):
                           p.certainty_threshold, p.valid_correspondence_threshold, p.roi_border_thickness], np.float64).tobytes())
         f.write(np.ascontiguousarray(sc.times, np.float64).tobytes()); f.write(sc.frames.tobytes())
     import torch
-    out = subprocess.run([exe, str(scene)], capture_output=True, text=True, timeout=120)
-    if not torch.cuda.is_available():
-        assert out.returncode == 1 and "no CPU fallback" in out.stderr and out.stdout == ""
-    else:
-        assert out.returncode == 0, out.stderr
+    assert os.path.exists(os.path.join(ROOT, "build", "ref_node_main.o"))          # node.cpp (main) compiles too
+    for mode in ([], ["nodelet"]):                                                # MPENode directly / through MPENodelet::onInit (nodelet.cpp)
+        out = subprocess.run([exe, str(scene)] + mode, capture_output=True, text=True, timeout=120)
+        if not torch.cuda.is_available():
+            # constructor, parameter server, CameraInfo and reconfigure callbacks ran; the first image needs the device
+            assert out.returncode == 1 and "no CPU fallback" in out.stderr and out.stdout == "", (mode, out.stderr)
+        else:
+            assert out.returncode == 0, out.stderr
