@@ -105,3 +105,38 @@ def test_tier1_is_conservative_on_adversarial_inputs(lib, fp32):
             assert S.max_root_dev < 1e-6 and S.max_pixel_dev < DEV_LIMIT[fp32][1], (case, tol, S.max_root_dev, S.max_pixel_dev)
             total += S.problems
     assert total > 100000
+
+
+@pytest.mark.parametrize("fp32", [1, 0])
+@pytest.mark.parametrize("name,focal_scale,size,z_range,object_scale", [
+    ("telephoto", 8.0, (752, 480), (4.0, 9.0), 1.0),            # huge fx: pixel errors scale with the focal length
+    ("wide", 1.0 / 3.0, (752, 480), (0.15, 0.4), 1.0),          # close range, strong perspective
+    ("1080p", None, (1920, 1080), (0.4, 1.2), 1.0),             # BASELINE config 3's camera (with its distortion)
+    ("far", 1.0, (752, 480), (3.0, 6.0), 1.0),                  # LEDs a few pixels apart: many hypotheses within the tolerance
+    ("large_object", 1.0, (752, 480), (3.0, 6.0), 8.0),
+])
+def test_tier1_is_conservative_for_other_cameras_and_object_sizes(lib, fp32, name, focal_scale, size, z_range, object_scale):
+    """The margin (0.25 px) and the flags were calibrated on the bench camera; the pre-test must stay conservative when the focal
+    length, the image size, the range or the object size change by an order of magnitude."""
+    lib.t1c_set_fp32(fp32)
+    W, H = size
+    if focal_scale is None:
+        K, D = synth.camera(W, H)
+    else:
+        K, D = synth.camera()
+        K = K.copy(); K[0, 0] *= focal_scale; K[1, 1] *= focal_scale
+        D = np.zeros(5)
+    mk = synth.markers(5) * object_scale
+    rng = np.random.default_rng(5)
+    dets = []
+    for _ in range(100):
+        T = synth.sample_pose(rng, K, D, mk, W, H, z_range=z_range)
+        _, und, _ = synth.project_distorted(K, D, T, mk)
+        det = und + rng.normal(size=und.shape) * 0.3
+        dets.append(det[rng.permutation(len(det))])
+    for tol in (1.0, 5.0):
+        S = run(lib, K, mk, dets, tol=tol)
+        assert S.violations == 0, (name, tol)
+        assert S.closest_call >= MARGIN * 0.99, (name, tol, S.closest_call)
+        assert S.max_root_dev < 1e-7 and S.max_pixel_dev < DEV_LIMIT[fp32][1], (name, tol, S.max_root_dev, S.max_pixel_dev)
+        assert S.voting_problems > 0 and S.survivors < 0.3 * S.problems
