@@ -61,7 +61,7 @@ def views(rng, K, D, mk, n, noise=0.3, junk=0):
     return out
 
 
-# fp32 = the shipped variant (MPE_T1_FP32: back-projection test in single precision), fp64 = everything in double
+# fp32 = the optional build (MPE_T1_FP32=1: back-projection test in single precision), fp64 = the default build, everything in double
 DEV_LIMIT = {1: (MARGIN * 4e-2, MARGIN * 0.2), 0: (MARGIN * 1e-2, MARGIN * 4e-2)}      # px: object views, adversarial inputs
 
 
