@@ -107,6 +107,7 @@ class ClockSampler:
         self.f.flush()
         per = {}                                   # GPU index -> (sm samples, max clocks, power samples)
         reasons = set()
+        per_reasons = {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.f.name) as fh:
             for line in fh.read().splitlines():
@@ -126,7 +127,8 @@ class ClockSampler:
                 sm.append(sm_v); mx.append(mx_v); pw.append(pw_v)
                 for n, v in zip(names, parts[6:10]):
                     if v.lower().startswith("active"):
-                        reasons.add(n if len(self.gpus) == 1 else f"{n}@gpu{idx}")
+                        reasons.add(n)                         # plain names in `reasons` (what the driver looks for) ...
+                        per_reasons.setdefault(idx, set()).add(n)   # ... which GPU it was goes into per_gpu
         if not per:
             out["error"] = "no nvidia-smi samples in the window"
         else:
@@ -134,7 +136,7 @@ class ClockSampler:
             out.update({"sm_mhz": min(med.values()), "sm_max_mhz": max(max(v[1]) for v in per.values()), "samples": sum(len(v[0]) for v in per.values()),
                         "power_w_max": max(max(v[2]) for v in per.values()), "window_s": round(t_end - t_begin, 3)})
             if len(self.gpus) > 1:                 # sm_mhz above is the slowest GPU's median
-                out["per_gpu"] = [{"gpu": i, "sm_mhz": med[i], "power_w_max": max(per[i][2])} for i in sorted(per)]
+                out["per_gpu"] = [{"gpu": i, "sm_mhz": med[i], "power_w_max": max(per[i][2]), "reasons": sorted(per_reasons.get(i, ()))} for i in sorted(per)]
         out["reasons"] = sorted(reasons)
         return out
 

@@ -46,7 +46,8 @@ def test_clock_window_several_gpus_reports_the_slowest_and_names_the_throttled_o
     w = _sampler([0, 1, 2, 3], txt).window(t0, t0 + 0.5)
     assert w["sm_mhz"] == 1700.0                                   # the slowest GPU's median
     assert [p["gpu"] for p in w["per_gpu"]] == [0, 1, 2, 3] and w["per_gpu"][2]["sm_mhz"] == 1700.0
-    assert w["reasons"] == ["sw_power_cap@gpu2"] and w["power_w_max"] == 330.0 and w["samples"] == 32
+    assert w["reasons"] == ["sw_power_cap"] and w["per_gpu"][2]["reasons"] == ["sw_power_cap"] and w["per_gpu"][0]["reasons"] == []
+    assert w["power_w_max"] == 330.0 and w["samples"] == 32
 
 
 def test_clock_window_without_samples_or_without_nvidia_smi():
